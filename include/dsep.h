@@ -1,0 +1,179 @@
+/*
+ * libdsep — C-ABI of the B200-native DiffSep reverse-diffusion hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*),
+ * launches asynchronously on that stream, allocates nothing that outlives the call, never
+ * synchronises, and returns 0 or a negative DSEP_ERR_* code (message via dsep_last_error()).
+ * Outputs are caller-allocated.  No torch types cross this boundary.
+ *
+ * What each function replaces in the reference (fakufaku/diffusion-separation @ d1855e9) is
+ * cited as file:line.  The reference's only native FFI on this path is the pybind11 op
+ *   upfirdn2d(Tensor in, Tensor kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ * (models/ncsnpp_utils/op/upfirdn2d.cpp:12-22); everything else it delegates to
+ * cuDNN/cuBLAS/cuFFT through PyTorch.  Those library calls are what the remaining entry points
+ * stand in for.  INTEGRATION.md shows the ctypes/pybind stubs a maintainer would add.
+ *
+ * Layouts: activations are channels-last, fp32 [B, H, W, C]; tensor-core operands are a pair of
+ * bf16 planes (hi, lo) with hi + lo == x to 2^-17 ("split" tensors) in the same [B, H, W, C]
+ * layout; waveforms are [B, C, T] fp32.
+ */
+#ifndef DSEP_H_
+#define DSEP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSEP_OK 0
+#define DSEP_ERR_INVALID (-1)     /* bad argument (the Python wrappers raise ValueError)      */
+#define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
+#define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
+
+#define DSEP_ABI_VERSION 1
+
+typedef void* dsep_stream_t; /* cudaStream_t */
+
+const char* dsep_last_error(void);
+int dsep_abi_version(void);
+/* 1 if the running device is sm_100 (B200); the product path refuses anything else. */
+int dsep_device_ok(void);
+
+/* ---- tensor-core convolution -------------------------------------------------------------
+ * out[b,h,w,n] = scale * ( sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c] + bias[n] + film[b,n]
+ *                          + residual[b,h,w,n] )
+ * Implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators).  ksize 3 (pad 1) or 1.  A is a split
+ * tensor [B,H,W,Cin] (Cin % 64 == 0); Wt a split tensor [ksize*ksize, Cout_pad, Cin] with
+ * Cout_pad in {16} or a multiple of 64; only the first cout_store channels are written, with
+ * row pitch cout_store.  passes = 3: hi*hi + lo*hi + hi*lo (fp32-grade); passes = 1: hi*hi.
+ * bias/film/residual may be NULL.  film is [B, film_stride] (pointer already offset to this
+ * layer's first channel).
+ * Replaces nn.Conv2d -> cuDNN in ddpm_conv3x3/ddpm_conv1x1 (models/ncsnpp_utils/layers.py:112-156),
+ * NIN (layers.py:678-689), Dense_0 bias add and the (x+h)/sqrt(2) residual (layerspp.py:311-323). */
+int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
+                   const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
+                   const float* bias, const float* film, int film_stride, const float* residual,
+                   float scale, float* out, int cout_store, int passes, dsep_stream_t stream);
+
+/* x (fp32, n elements) -> split bf16 planes. */
+int dsep_split_bf16(const float* x, int64_t n, void* hi, void* lo, dsep_stream_t stream);
+
+/* ---- GroupNorm / SiLU / FIR resampling ------------------------------------------------------
+ * Channel-concatenated input [x0 (C0 ch) | x1 (C1 ch)] (x1 may be NULL, C1 = 0), pixels P=H*W.
+ * stats is double [B, groups, 2] = (sum, sum of squares), zeroed and filled by dsep_gn_stats.
+ * Replaces nn.GroupNorm(min(C//4,32), eps=1e-6) + nn.SiLU (layerspp.py:264-266,292; ncsnpp.py:253-258)
+ * and torch.cat([h, hs.pop()]) (ncsnpp.py:411). */
+int dsep_gn_stats(const float* x0, int C0, const float* x1, int C1, int B, int P, int groups,
+                  double* stats, dsep_stream_t stream);
+/* a = act(GN(x)) as split planes (act: 0 none, 1 SiLU); optionally also the raw x as split
+ * planes (r_hi/r_lo, for the 1x1 shortcut conv) — all in the concatenated channel layout. */
+int dsep_gn_act_split(const float* x0, int C0, const float* x1, int C1, int B, int P, int groups,
+                      const double* stats, const float* gamma, const float* beta, float eps, int act,
+                      void* a_hi, void* a_lo, void* r_hi, void* r_lo, dsep_stream_t stream);
+/* 2x FIR resampling with taps [1,3,3,1] of an fp32 [B,H,W,C] tensor (mode 1: up, 2: down).
+ * Outputs (each nullable pair): a = FIR(act(GN(x))) split, r = FIR(x) split, y = FIR(x) fp32.
+ * stats/gamma/beta NULL => no GroupNorm branch.
+ * Replaces upsample_2d/downsample_2d (models/ncsnpp_utils/up_or_down_sampling.py:206-273)
+ * -> upfirdn2d (op/upfirdn2d.py:145-156, upfirdn2d_kernel.cu:107-369). */
+int dsep_fir_resample(const float* x, int B, int H, int W, int C, int mode, int groups,
+                      const double* stats, const float* gamma, const float* beta, float eps,
+                      void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y, dsep_stream_t stream);
+/* Drop-in for the reference's own FFI signature on its own layout: in [planes, H, W] fp32,
+ * kernel fixed to outer([1,3,3,1])/16*up^2; supports exactly the two calls the model makes
+ * (up=2,down=1,pad=(2,1)) and (up=1,down=2,pad=(1,1)); anything else -> DSEP_ERR_UNSUPPORTED.
+ * Replaces upfirdn2d_op (upfirdn2d_kernel.cu:209-369) as bound in upfirdn2d.cpp:12-22. */
+int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_x, int up_y, int down_x,
+                   int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, float* out,
+                   dsep_stream_t stream);
+
+/* out = h + bias + conv1x1(pyr): Combine(method="sum") (layerspp.py:52-57). pyr fp32 [B,P,Cp],
+ * w fp32 [C,Cp]. */
+int dsep_combine(const float* pyr, int Cp, const float* w, const float* bias, const float* h,
+                 float* out, int B, int P, int C, dsep_stream_t stream);
+/* y = a + b (fp32, n elements): pyramid accumulation (ncsnpp.py:440). */
+int dsep_add(const float* a, const float* b, float* y, int64_t n, dsep_stream_t stream);
+
+/* ---- attention ---------------------------------------------------------------------------
+ * qkv fp32 [B,S,3C] (q | k | v per token); o = softmax(q k^T * scale) v written as split planes
+ * [B,S,C].  Replaces the two einsums + softmax of AttnBlockpp.forward (layerspp.py:83-88). */
+int dsep_attention(const float* qkv, int B, int S, int C, float scale, void* o_hi, void* o_lo,
+                   dsep_stream_t stream);
+
+/* ---- time embedding -------------------------------------------------------------------------
+ * temb_act = SiLU(Linear2(SiLU(Linear1([sin,cos](log(t) * Wf * 2 * pi))))) -> [B, 4nf]
+ * (ncsnpp.py:324-343, layerspp.py:39-41; the SiLU every block applies first is folded in). */
+int dsep_time_embedding(const float* t, const float* Wf, const float* w1, const float* b1,
+                        const float* w2, const float* b2, int B, int nf, float* temb_act,
+                        dsep_stream_t stream);
+/* film[b, r] = sum_d temb_act[b,d] * Wd[r,d] + bd[r] for all ResBlocks' stacked Dense_0 rows
+ * (layerspp.py:311-313). */
+int dsep_film(const float* temb_act, const float* Wd, const float* bd, int B, int D, int R,
+              float* film, dsep_stream_t stream);
+
+/* ---- STFT-510 / iSTFT ---------------------------------------------------------------------
+ * Framing exactly as torch.stft(n_fft=510, hop=128, center=True, pad_mode="constant") on the
+ * signal right-padded by 382 zeros (score_models.py:107-112): frame f covers samples
+ * [128 f - 255, 128 f + 255), zero outside [0,T), times periodic Hann(510).
+ * frames: fp32 [B*C*Fr, 512] (columns 510, 511 zero).  x: [B, C, T]. */
+int dsep_stft_frames(const float* x, int B, int C, int T, int Fr, float* frames, dsep_stream_t stream);
+/* C[M,N] = A[M,K] * Bm[K,N], fp32 FFMA, row-major, leading dimensions in elements.
+ * Used with the DFT-510 basis in place of cuFFT (torch.stft/istft). */
+int dsep_sgemm(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N,
+               int K, dsep_stream_t stream);
+/* dft [B*Cw*Fr, 512] (re,im interleaved per bin) -> network input, channels-last:
+ * |S|^e e^{j arg S} * factor (score_models.py:41-48), channel order [re_0..re_{Cw-1}, im_0..]
+ * (:72-76), frames zero-padded to Wp (:83-91), then 2x-1 (ncsnpp.py:347-349).
+ * chan0/Ctot let the xt channels and the (hoisted, step-invariant) mix channel be written by
+ * separate calls: source channel c of this call lands in real slot chan0+c, imag slot
+ * Ctot+chan0+c.  x_f32: [B,256,Wp,2*Ctot]; a_hi/a_lo: [B,256,Wp,Cpad] split (Cpad>=2*Ctot,
+ * extra channels must be pre-zeroed by the caller). */
+int dsep_spec_pack(const float* dft, int B, int Cw, int Fr, int Wp, int chan0, int Ctot, int Cpad,
+                   float factor, float exponent, float* x_f32, void* a_hi, void* a_lo,
+                   dsep_stream_t stream);
+/* pyramid [B,256,Wp,Cp] fp32 -> /t[b] -> conv1x1 Cp->2*nsrc (ncsnpp.py:472-477) -> complex
+ * [re_s, im_s] (score_models.py:78-81) -> /factor, |S|^{1/e} e^{j arg S} (:59-64) -> spec
+ * [B*nsrc*Fr, 512] (re,im interleaved, frames beyond Fr dropped). */
+int dsep_out_head(const float* pyr, int B, int Wp, int Cp, int nsrc, int Fr, const float* t,
+                  const float* w, const float* bias, float factor, float exponent, float* spec,
+                  dsep_stream_t stream);
+/* frames_t [B*C*Fr, 512] (time-domain frames from the inverse basis) -> window, overlap-add,
+ * divide by the squared-window envelope, drop 255 samples each side, crop / zero-pad to T
+ * (torch.istft; score_models.py:122-123, :99-105).  out [B,C,T]. */
+int dsep_istft_ola(const float* frames_t, int B, int C, int Fr, int T, float* out, dsep_stream_t stream);
+
+/* ---- SDE arithmetic -------------------------------------------------------------------------
+ * All on x [B,2,T].  t is a device array [B].  sigma_mix [B,T] is NULL for MixSDE and
+ * PriorMixSDE._std_sigma_mix(mix) for PriorMixSDE.  noise may be NULL: then N(0,1) samples
+ * are drawn in-kernel (Philox4x32-10, Box-Muller) from (seed, offset).
+ * prior:      x = 0.5 mix + L(T) z                         (sdes/sdes.py:334-346, 564-587)
+ * corrector:  xm = x + 2 snr^2 L L score ; x' = xm + 2 snr L z   (sdes/correctors.py:109-128)
+ * predictor:  xm = x + lambda dt (x - mean_c x) + G^2 score ; x' = xm + G z, G = g(t) sqrt(dt)
+ *             (sdes/predictors.py:60-66, sdes/sdes.py:93-107,163-171,275-284) */
+typedef struct {
+    float d_lambda, sigma_min, sigma_max, T_end;
+} dsep_sde_params;
+int dsep_sde_prior(const dsep_sde_params* p, const float* mix, const float* sigma_mix,
+                   const float* noise, uint64_t seed, uint64_t offset, int B, int T, float* x,
+                   dsep_stream_t stream);
+int dsep_sde_corrector(const dsep_sde_params* p, const float* x, const float* score, const float* t,
+                       const float* sigma_mix, const float* noise, uint64_t seed, uint64_t offset,
+                       float snr, int B, int T, float* x_out, float* x_mean, dsep_stream_t stream);
+int dsep_sde_predictor(const dsep_sde_params* p, const float* x, const float* score, const float* t,
+                       const float* sigma_mix, const float* noise, uint64_t seed, uint64_t offset,
+                       float dt, int B, int T, float* x_out, float* x_mean, dsep_stream_t stream);
+/* PriorMixSDE._std_sigma_mix (sdes/sdes.py:477-489): 0.5 sqrt(clamp(avgpool_k(mix^2), 1e-4)). */
+int dsep_sigma_mix(const float* mix, int B, int T, int avg_len, float* sigma, dsep_stream_t stream);
+/* normalize_batch (pl_model.py:81-88): per-utterance (x - mean) / clamp(std_unbiased, 1e-5). */
+int dsep_normalize(const float* mix, int B, int n, float* out, float* mean, float* std,
+                   dsep_stream_t stream);
+/* scale_output (separate.py:73-78): sep * <mix,sep> / sum(sep^2 + 1e-10), per (b, source). */
+int dsep_scale_output(const float* mix, const float* sep, int B, int nsrc, int T, float* out,
+                      dsep_stream_t stream);
+/* z ~ N(0,1), n elements, Philox4x32-10 keyed by (seed, offset). */
+int dsep_randn(float* z, int64_t n, uint64_t seed, uint64_t offset, dsep_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSEP_H_ */

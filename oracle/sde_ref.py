@@ -1,0 +1,158 @@
+"""ORACLE (test infrastructure, not product code): closed-form restatement of the DiffSep
+SDE arithmetic and of the predictor-corrector sampler loop.
+
+Restates (reference file:line):
+  * MixSDE            sdes/sdes.py:180-349   (sde :275-284, _cov_eigval :296-310, _std :316-320,
+                                               prior_sampling :334-346)
+  * PriorMixSDE       sdes/sdes.py:352-590   (_std_sigma_mix :477-489, sde :451-470, _std :515-528,
+                                               prior_sampling :564-587)
+  * SDE.discretize / RSDE.discretize          sdes/sdes.py:93-107, 163-171
+  * ReverseDiffusionPredictor.update_fn       sdes/predictors.py:60-66
+  * AnnealedLangevinDynamics2.update_fn       sdes/correctors.py:109-128
+  * get_pc_sampler / get_pc_scheduled_sampler sdes/__init__.py:46-190
+
+With ``A`` the channel-averaging matrix and ``Pn = I - A`` (sdes.py:242-248), for any
+``v`` [B, C, T] and channel mean ``vbar``:  ``A v = vbar``, ``Pn v = v - vbar`` and
+``(a A + b Pn) v = a vbar + b (v - vbar)``.
+
+Noise is *injected* (a list of pre-drawn tensors popped in draw order: prior, then per step
+[corrector noise]*n_steps, predictor z) because ``randn_like`` on the reference's strided
+tensors does not map seeds to elements reproducibly.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+class MixSDEParams:
+    def __init__(self, ndim=2, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5, N=30,
+                 prior=False, avg_len=510):
+        self.ndim, self.d_lambda = ndim, d_lambda
+        self.sigma_min, self.sigma_max = sigma_min, sigma_max
+        self.ratiosig = sigma_max / sigma_min
+        self.logsig = math.log(self.ratiosig)
+        self.N = N
+        self.T = 1.0
+        self.prior = prior            # True -> PriorMixSDE
+        self.avg_len = avg_len
+
+
+def cov_eigval(p, t):
+    """sdes.py:296-310 / 497-511."""
+    mult = p.sigma_min ** 2
+    srp = p.ratiosig ** (2 * t)
+    ev1 = mult * (srp - 1)
+    ev2 = mult * (srp - torch.exp(-2.0 * p.d_lambda * t)) / (1.0 + p.d_lambda / p.logsig)
+    return ev1, ev2
+
+
+def sigma_mix(p, mix):
+    """PriorMixSDE._std_sigma_mix, sdes.py:477-489."""
+    s = F.avg_pool1d(mix ** 2, kernel_size=p.avg_len, stride=1, padding=p.avg_len // 2)
+    s = s.clamp(min=1e-4).sqrt()
+    if p.avg_len % 2 == 0:
+        s = s[..., :-1]
+    return 0.5 * s
+
+
+def mult_L(p, t, v, mix=None):
+    """L(t) v with L = sqrt(ev1) A + sqrt(ev2) Pn [* sigma_mix]; sdes.py:316-328 / 515-532."""
+    ev1, ev2 = cov_eigval(p, t)
+    vbar = v.mean(dim=1, keepdim=True)
+    out = ev1.sqrt()[:, None, None] * vbar + ev2.sqrt()[:, None, None] * (v - vbar)
+    if p.prior:
+        out = out * sigma_mix(p, mix)
+    return out
+
+
+def prior_sampling(p, mix, z):
+    """x_T = 0.5 mix (broadcast to ndim channels) + L(T) z; sdes.py:334-346 / 564-587."""
+    t = torch.ones(mix.shape[0], dtype=mix.dtype) * p.T
+    mean = torch.broadcast_to(0.5 * mix, (mix.shape[0], p.ndim, mix.shape[2]))
+    return mean + mult_L(p, t, z, mix)
+
+
+def diffusion(p, t, mix=None):
+    """g(t) = sigma_min ratiosig^t sqrt(2 logsig) [* sigma_mix]; sdes.py:282-283 / 465-469."""
+    g = p.sigma_min * p.ratiosig ** t * math.sqrt(2 * p.logsig)
+    g = g[:, None, None]
+    if p.prior:
+        g = g * sigma_mix(p, mix)
+    return g
+
+
+def predictor_step(p, score_fn, x, t, mix, z):
+    """reverse_diffusion predictor: predictors.py:60-66 with RSDE.discretize sdes.py:163-171.
+
+    dt is always 1/N (``getattr(kwargs, "dt", ...)`` on a dict)."""
+    dt = 1.0 / p.N
+    xbar = x.mean(dim=1, keepdim=True)
+    drift = -p.d_lambda * (x - xbar)
+    f = drift * dt
+    G = diffusion(p, t, mix) * math.sqrt(dt)
+    rev_f = f - G ** 2 * score_fn(x, t, mix)
+    x_mean = x - rev_f
+    return x_mean + G * z, x_mean
+
+
+def corrector_step(p, score_fn, x, t, mix, noises, snr):
+    """ald2: correctors.py:109-128.  ``noises``: list of n_steps tensors."""
+    x_mean = x
+    for nz in noises:
+        grad = score_fn(x, t, mix)
+        g2 = mult_L(p, t, mult_L(p, t, grad, mix), mix)
+        x_mean = x + 2 * snr ** 2 * g2
+        x = x_mean + 2 * snr * mult_L(p, t, nz, mix)
+    return x, x_mean
+
+
+def timesteps(p, eps, schedule=None, dtype=torch.float32):
+    """sdes/__init__.py:175 (plain) and :92-111 (scheduled; N+1 points, dt unchanged)."""
+    if schedule is None:
+        return torch.linspace(p.T, eps, p.N, dtype=dtype)
+    if schedule == "linear":
+        return torch.linspace(p.T, eps, p.N + 1, dtype=dtype)
+    if schedule == "log":
+        return torch.logspace(math.log(p.T) / math.log(10), math.log(eps) / math.log(10),
+                              p.N + 1, base=10, dtype=dtype)
+    if schedule == "revlog":
+        return torch.logspace(math.log(eps) / math.log(10), math.log(p.T) / math.log(10),
+                              p.N + 1, base=10, dtype=dtype).flip(dims=(0,))
+    raise NotImplementedError(f"Schedule '{schedule}' does not exist")
+
+
+def pc_sampler(p, score_fn, mix, noises, eps=0.03, snr=0.5, corrector_steps=1,
+               denoise=True, schedule=None, intermediate=False):
+    """sdes/__init__.py:166-190.  ``noises``: flat list in draw order."""
+    noises = list(noises)
+    xt = prior_sampling(p, mix, noises.pop(0))
+    ts = timesteps(p, eps, schedule, mix.dtype)
+    im = []
+    xt_mean = xt
+    for i in range(p.N):
+        vec_t = torch.ones(mix.shape[0], dtype=mix.dtype) * ts[i]
+        cn = [noises.pop(0) for _ in range(corrector_steps)]
+        xt, xt_mean_c = corrector_step(p, score_fn, xt, vec_t, mix, cn, snr)
+        if intermediate:
+            im.append((xt, xt_mean_c))
+        xt, xt_mean = predictor_step(p, score_fn, xt, vec_t, mix, noises.pop(0))
+    out = xt_mean if denoise else xt
+    nfe = p.N * (corrector_steps + 1)
+    return (out, nfe, im) if intermediate else (out, nfe)
+
+
+def normalize_batch(mix):
+    """pl_model.py:81-88 (unbiased std, clamp 1e-5)."""
+    mean = mix.mean(dim=(1, 2), keepdim=True)
+    std = mix.std(dim=(1, 2), keepdim=True).clamp(min=1e-5)
+    return (mix - mean) / std, mean, std
+
+
+def scale_output(mix, sep):
+    """separate.py:73-78."""
+    num = (mix * sep).sum(dim=-1, keepdim=True)
+    den = (sep * sep + 1e-10).sum(dim=-1, keepdim=True)
+    return num / den * sep
