@@ -1,0 +1,93 @@
+"""ctypes binding of ``libdsep.so`` — the C-ABI declared in ``include/dsep.h``.
+
+There is no fallback: if the library is missing or a call fails, the caller gets an exception.
+``DSEP_ERR_INVALID`` maps to ``ValueError`` and ``DSEP_ERR_UNSUPPORTED`` to ``NotImplementedError``
+(what the reference raises for bad arguments / unsupported SDEs), CUDA errors to ``RuntimeError``
+(what a failed ``TORCH_CHECK`` in the reference's pybind11 ops raises).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libdsep.so"
+
+ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
+ABI_VERSION = 1
+
+_p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
+
+
+class SdeParams(C.Structure):
+    _fields_ = [("d_lambda", C.c_float), ("sigma_min", C.c_float), ("sigma_max", C.c_float),
+                ("T_end", C.c_float)]
+
+
+# name -> argument types, exactly the prototypes of include/dsep.h (return type int)
+PROTOTYPES = {
+    "dsep_conv2d_tc": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _f, _f, _p, _i, _i, _p],
+    "dsep_split_f16": [_p, _i64, _f, _p, _p, _p],
+    "dsep_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _p, _p],
+    "dsep_gn_act_split": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p],
+    "dsep_fir_resample": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
+    "dsep_upfirdn2d": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "dsep_combine": [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p],
+    "dsep_add": [_p, _p, _p, _i64, _p],
+    "dsep_attention": [_p, _i, _i, _i, _f, _p, _p, _p],
+    "dsep_time_embedding": [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p],
+    "dsep_film": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "dsep_stft_frames": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "dsep_sgemm": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
+    "dsep_spec_pack": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
+    "dsep_out_head": [_p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _f, _p, _p],
+    "dsep_istft_ola": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "dsep_sde_prior": [C.POINTER(SdeParams), _p, _p, _p, _u64, _u64, _i, _i, _p, _p],
+    "dsep_sde_corrector": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
+    "dsep_sde_predictor": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
+    "dsep_sigma_mix": [_p, _i, _i, _i, _p, _p],
+    "dsep_normalize": [_p, _i, _i, _p, _p, _p, _p],
+    "dsep_scale_output": [_p, _p, _i, _i, _i, _p, _p],
+    "dsep_randn": [_p, _i64, _u64, _u64, _p],
+}
+OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok")
+
+_lib = None
+
+
+def load():
+    """Loads libdsep.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m diffsep_b200.build` "
+            "(there is no CPU or PyTorch fallback for the DiffSep hot path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.dsep_last_error.restype = C.c_char_p
+    lib.dsep_last_error.argtypes = []
+    lib.dsep_abi_version.restype = C.c_int
+    lib.dsep_device_ok.restype = C.c_int
+    if lib.dsep_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libdsep.so ABI {lib.dsep_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, name: str = "dsep"):
+    if rc == 0:
+        return
+    msg = load().dsep_last_error().decode("utf-8", "replace")
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"{name}: {msg} (code {rc})")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,7 +1,7 @@
 // Shared device/host helpers for the DiffSep B200 kernels (sm_100a only).
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -57,10 +57,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, 0x989680;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, P;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
@@ -108,8 +108,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)
                  : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, single CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate, single CTA.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -160,19 +160,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= 2ull << 61;                                         // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-           (static_cast<uint32_t>(M >> 4) << 24);
+// Instruction descriptor (kind::f16): fp16 x fp16 -> fp32 (c_format = 1 at bit 4, a/b_format = 0
+// at bits 7/10), both operands K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---- numerics shared by the element-wise kernels
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
-// fp32 -> (hi, lo) bf16 pair with hi + lo == x to ~2^-17 relative.
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// fp32 -> (hi, lo) fp16 pair with hi + lo == x to ~2^-22 relative (11 + 11 significand bits) while
+// |x| is in fp16's normal range; below it the error is bounded by 2^-25 absolute.  Three
+// tensor-core products hi*hi + lo*hi + hi*lo then reproduce the fp32 product to ~2^-21.
+// Values are clamped to +-60000 so an out-of-range activation saturates instead of becoming NaN.
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    x = fminf(fmaxf(x, -60000.0f), 60000.0f);
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
 }
 
 }  // namespace dsep

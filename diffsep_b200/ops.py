@@ -1,0 +1,194 @@
+"""Tensor-level wrappers over the C-ABI (``_lib``): each takes CUDA tensors the caller allocated,
+checks layout on the host, and launches on torch's current stream.  PyTorch is only the
+allocator / stream provider here; no torch operator computes anything on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import SdeParams, call
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("dsep ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError("dsep ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def require_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("diffsep_b200 needs a CUDA device (B200, sm_100); no CPU fallback exists")
+    if not _lib.load().dsep_device_ok():
+        raise RuntimeError("diffsep_b200 kernels are built for sm_100a (B200) only")
+
+
+def _f32(t, name):
+    if t is not None and t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+class Split:
+    """A pair of fp16 planes (hi, lo) with hi + lo == x: a tensor-core operand."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device):
+        return Split(torch.empty(shape, dtype=torch.float16, device=device),
+                     torch.empty(shape, dtype=torch.float16, device=device))
+
+    @staticmethod
+    def zeros(shape, device):
+        return Split(torch.zeros(shape, dtype=torch.float16, device=device),
+                     torch.zeros(shape, dtype=torch.float16, device=device))
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+
+def split_f16(x, out: Split, prescale=1.0):
+    _f32(x, "x")
+    call("dsep_split_f16", ptr(x), x.numel(), prescale, ptr(out.hi), ptr(out.lo), stream())
+    return out
+
+
+def conv2d_tc(a: Split, B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store, bias=None, film=None,
+              film_stride=0, residual=None, scale=1.0, acc_scale=1.0, passes=3):
+    _f32(out, "out"); _f32(bias, "bias"); _f32(film, "film"); _f32(residual, "residual")
+    call("dsep_conv2d_tc", ptr(a.hi), ptr(a.lo), B, H, W, Cin, ptr(w.hi), ptr(w.lo), cout_pad, ksize,
+         ptr(bias), film.data_ptr() if film is not None else None, film_stride, ptr(residual),
+         scale, acc_scale, ptr(out), cout_store, passes, stream())
+    return out
+
+
+def gn_stats(x0, C0, x1, C1, B, P, groups, stats):
+    if stats.dtype != torch.float64:
+        raise ValueError("stats must be float64 [B, groups, 2]")
+    call("dsep_gn_stats", ptr(_f32(x0, "x0")), C0, ptr(_f32(x1, "x1")), C1, B, P, groups, ptr(stats), stream())
+    return stats
+
+
+def gn_act_split(x0, C0, x1, C1, B, P, groups, stats, gamma, beta, eps, act, a: Split = None, r: Split = None):
+    call("dsep_gn_act_split", ptr(x0), C0, ptr(x1), C1, B, P, groups, ptr(stats), ptr(gamma), ptr(beta), eps,
+         act, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
+         ptr(r.lo) if r else None, stream())
+
+
+def fir_resample(x, B, H, W, Cc, mode, groups=0, stats=None, gamma=None, beta=None, eps=1e-6, a: Split = None,
+                 r: Split = None, y=None):
+    call("dsep_fir_resample", ptr(_f32(x, "x")), B, H, W, Cc, mode, groups, ptr(stats), ptr(gamma), ptr(beta),
+         eps, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
+         ptr(r.lo) if r else None, ptr(y), stream())
+
+
+def upfirdn2d_planes(x, planes, H, W, up, down, pad, out):
+    call("dsep_upfirdn2d", ptr(_f32(x, "x")), planes, H, W, up, up, down, down, pad[0], pad[1], pad[0], pad[1],
+         ptr(out), stream())
+    return out
+
+
+def combine(pyr, Cp, w, bias, h, out, B, P, Cc):
+    call("dsep_combine", ptr(pyr), Cp, ptr(w), ptr(bias), ptr(h), ptr(out), B, P, Cc, stream())
+    return out
+
+
+def add(a, b, y):
+    call("dsep_add", ptr(a), ptr(b), ptr(y), a.numel(), stream())
+    return y
+
+
+def attention(qkv, B, S, Cc, scale, o: Split):
+    call("dsep_attention", ptr(_f32(qkv, "qkv")), B, S, Cc, scale, ptr(o.hi), ptr(o.lo), stream())
+
+
+def time_embedding(t, Wf, w1, b1, w2, b2, B, nf, out):
+    call("dsep_time_embedding", ptr(_f32(t, "t")), ptr(Wf), ptr(w1), ptr(b1), ptr(w2), ptr(b2), B, nf,
+         ptr(out), stream())
+    return out
+
+
+def film(temb_act, Wd, bd, B, D, R, out):
+    call("dsep_film", ptr(temb_act), ptr(Wd), ptr(bd), B, D, R, ptr(out), stream())
+    return out
+
+
+def stft_frames(x, window, B, Cc, T, Fr, frames):
+    call("dsep_stft_frames", ptr(_f32(x, "x")), ptr(window), B, Cc, T, Fr, ptr(frames), stream())
+    return frames
+
+
+def sgemm(A, lda, Bm, ldb, Cm, ldc, M, N, K):
+    call("dsep_sgemm", ptr(A), lda, ptr(Bm), ldb, ptr(Cm), ldc, M, N, K, stream())
+    return Cm
+
+
+def spec_pack(dft, B, Cw, Fr, Wp, chan0, Ctot, Cpad, factor, exponent, x_f32, a: Split):
+    call("dsep_spec_pack", ptr(dft), B, Cw, Fr, Wp, chan0, Ctot, Cpad, factor, exponent, ptr(x_f32),
+         ptr(a.hi) if a else None, ptr(a.lo) if a else None, stream())
+
+
+def out_head(pyr, B, Wp, Cp, nsrc, Fr, t, w, bias, factor, exponent, spec):
+    call("dsep_out_head", ptr(pyr), B, Wp, Cp, nsrc, Fr, ptr(_f32(t, "t")), ptr(w), ptr(bias), factor, exponent,
+         ptr(spec), stream())
+    return spec
+
+
+def istft_ola(frames_t, window, B, Cc, Fr, T, out):
+    call("dsep_istft_ola", ptr(frames_t), ptr(window), B, Cc, Fr, T, ptr(out), stream())
+    return out
+
+
+def sde_params(d_lambda, sigma_min, sigma_max, T_end=1.0):
+    return SdeParams(float(d_lambda), float(sigma_min), float(sigma_max), float(T_end))
+
+
+def sde_prior(p, mix, sigma_mix, noise, seed, offset, B, T, x):
+    call("dsep_sde_prior", C.byref(p), ptr(_f32(mix, "mix")), ptr(sigma_mix), ptr(_f32(noise, "noise")), seed,
+         offset, B, T, ptr(x), stream())
+    return x
+
+
+def sde_corrector(p, x, score, t, sigma_mix, noise, seed, offset, snr, B, T, x_out, x_mean):
+    call("dsep_sde_corrector", C.byref(p), ptr(_f32(x, "x")), ptr(_f32(score, "score")), ptr(_f32(t, "t")),
+         ptr(sigma_mix), ptr(_f32(noise, "noise")), seed, offset, snr, B, T, ptr(x_out), ptr(x_mean), stream())
+
+
+def sde_predictor(p, x, score, t, sigma_mix, noise, seed, offset, dt, B, T, x_out, x_mean):
+    call("dsep_sde_predictor", C.byref(p), ptr(_f32(x, "x")), ptr(_f32(score, "score")), ptr(_f32(t, "t")),
+         ptr(sigma_mix), ptr(_f32(noise, "noise")), seed, offset, dt, B, T, ptr(x_out), ptr(x_mean), stream())
+
+
+def sigma_mix(mix, B, T, avg_len, out):
+    call("dsep_sigma_mix", ptr(_f32(mix, "mix")), B, T, avg_len, ptr(out), stream())
+    return out
+
+
+def normalize(mix, B, n, out, mean=None, std=None):
+    call("dsep_normalize", ptr(_f32(mix, "mix")), B, n, ptr(out), ptr(mean), ptr(std), stream())
+    return out
+
+
+def scale_output(mix, sep, B, nsrc, T, out):
+    call("dsep_scale_output", ptr(_f32(mix, "mix")), ptr(_f32(sep, "sep")), B, nsrc, T, ptr(out), stream())
+    return out
+
+
+def randn(z, seed, offset):
+    call("dsep_randn", ptr(_f32(z, "z")), z.numel(), seed, offset, stream())
+    return z

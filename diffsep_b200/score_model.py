@@ -1,0 +1,191 @@
+"""``ScoreModelNCSNpp``: waveform -> STFT -> NCSN++ -> iSTFT, the score network of DiffSep.
+
+Keeps the reference's constructor arguments and ``forward(xt, time, mix)`` signature
+(``models/score_models.py:10-138``); everything inside runs in libdsep kernels:
+
+  pre_process  (:107-116)  frames (window, centre padding, right padding by n_fft-hop) -> real DFT-510
+                           as an fp32 GEMM against a precomputed basis -> |S|^e e^{j arg S} * factor,
+                           re/im channel stacking, frame padding to x64 and the backbone's 2x-1
+                           affine, written straight as tensor-core operand planes + the fp32 pyramid
+  backbone                 ``NCSNppB200``
+  post_process (:118-124)  /t, output 1x1 conv, complex packing, decompression -> inverse real DFT
+                           (GEMM) -> windowed overlap-add / window envelope, crop to T
+
+The mixture's spectrogram channel does not change during sampling, so it is computed once per
+mixture tensor and reused by every evaluation (the reference recomputes it 60 times per utterance).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import torch
+
+from . import ops
+from .backbone import NCSNppB200
+from .ops import Split
+
+N_BINS = 256
+LD = 512   # padded frame / spectrum row length
+
+
+def n_frames(T, n_fft=510, hop=128):
+    return 1 + (T + (n_fft - hop)) // hop
+
+
+def _dft_bases(n_fft, device):
+    """Forward basis [LD, LD]: column 2k = cos(2 pi k n / n_fft), 2k+1 = -sin(...); rows >= n_fft zero.
+    Inverse basis [LD, LD]: row 2k / 2k+1 = c_k cos / -c_k sin over n, c_0 = c_{n_fft/2} = 1/n_fft,
+    else 2/n_fft (one-sided irfft; imaginary parts of DC and Nyquist are ignored like torch.istft)."""
+    n = torch.arange(n_fft, dtype=torch.float64)
+    k = torch.arange(N_BINS, dtype=torch.float64)
+    ang = 2.0 * math.pi * torch.outer(n, k) / n_fft        # [n, k]
+    fwd = torch.zeros(LD, LD, dtype=torch.float64)
+    fwd[:n_fft, 0::2] = torch.cos(ang)
+    fwd[:n_fft, 1::2] = -torch.sin(ang)
+    ck = torch.full((N_BINS,), 2.0 / n_fft, dtype=torch.float64)
+    ck[0] = 1.0 / n_fft
+    ck[n_fft // 2] = 1.0 / n_fft
+    inv = torch.zeros(LD, LD, dtype=torch.float64)
+    inv[0::2, :n_fft] = (torch.cos(ang) * ck).t()
+    inv[1::2, :n_fft] = (-torch.sin(ang) * ck).t()
+    inv[1, :] = 0.0
+    inv[2 * (n_fft // 2) + 1, :] = 0.0
+    return fwd.to(torch.float32).to(device), inv.to(torch.float32).to(device)
+
+
+class ScoreModelNCSNpp(torch.nn.Module):
+    """Drop-in for the reference class of the same name (inference only)."""
+
+    def __init__(self, num_sources=2, stft_args=None, backbone_args=None, transform="exponent",
+                 spec_abs_exponent=0.5, spec_factor=0.15, spec_trans_learnable=False,
+                 state_dict=None, device="cuda", passes=3, **kwargs):
+        super().__init__()
+        stft_args = dict(stft_args or dict(n_fft=510, hop_length=128, center=True, pad_mode="constant"))
+        if stft_args.get("n_fft", 510) != 510 or stft_args.get("hop_length", 128) != 128:
+            raise NotImplementedError("the B200 path implements the reference's n_fft=510 / hop=128 STFT")
+        if not stft_args.get("center", True) or stft_args.get("pad_mode", "constant") != "constant":
+            raise NotImplementedError("only center=True, pad_mode='constant' (reference default.yaml:18-22)")
+        if transform not in ("exponent", "none"):
+            raise NotImplementedError(f"transform '{transform}' (reference uses 'exponent')")
+        if spec_trans_learnable:
+            raise NotImplementedError("spec_trans_learnable is a training feature")
+        ops.require_device()
+        self.num_sources = num_sources
+        self.n_fft, self.hop = 510, 128
+        self.spec_abs_exponent = float(abs(spec_abs_exponent)) if transform == "exponent" else 1.0
+        self.spec_factor = float(spec_factor)
+        backbone_args = dict(backbone_args or {})
+        backbone_args.pop("_target_", None)
+        self.nf = int(backbone_args.pop("nf", 128))
+        if backbone_args:
+            unsupported = {k: v for k, v in backbone_args.items() if k not in _BACKBONE_DEFAULTS
+                           or _BACKBONE_DEFAULTS[k] != v}
+            if unsupported:
+                raise NotImplementedError(f"backbone options outside the hot path: {unsupported}")
+        self.dev = torch.device(device)
+        self.passes = passes
+        self.ch_in = 2 * num_sources + 2
+        self.ch_out = 2 * num_sources
+        self.backbone = None
+        self.window = torch.hann_window(self.n_fft, dtype=torch.float32).to(self.dev)
+        self.basis_fwd, self.basis_inv = _dft_bases(self.n_fft, self.dev)
+        self._bufs = {}
+        self._mix_cache = None     # (data_ptr, B, T) of the mixture whose spectrogram is resident
+        self._mix_cache_on = False
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # -------------------------------------------------------------- weights
+    def load_state_dict(self, state_dict, strict=True):
+        """Accepts the reference layout: ``backbone.*`` (+ ``stft.window``, ``stft_inv.window``)."""
+        bb = {k[len("backbone."):]: v for k, v in state_dict.items() if k.startswith("backbone.")}
+        if not bb:
+            bb = dict(state_dict)
+        if "stft.window" in state_dict:
+            self.window = state_dict["stft.window"].detach().to(self.dev, torch.float32).contiguous()
+        self.backbone = NCSNppB200(bb, nf=self.nf, ch_in=self.ch_in, ch_out=self.ch_out, device=self.dev,
+                                   passes=self.passes)
+        return self
+
+    # -------------------------------------------------------------- buffers per (B, T)
+    def _work(self, B, T):
+        key = (B, T)
+        if key in self._bufs:
+            return self._bufs[key]
+        dev, ns = self.dev, self.num_sources
+        Fr = n_frames(T)
+        Wp = (Fr + 63) // 64 * 64
+        f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        b = dict(
+            Fr=Fr, Wp=Wp,
+            frames=f32(B * ns * Fr, LD), dft=f32(B * ns * Fr, LD),
+            frames_mix=f32(B * Fr, LD), dft_mix=f32(B * Fr, LD),
+            x_planes=Split.zeros((B, N_BINS, Wp, 64), dev),
+            x_pyr=f32(B, N_BINS, Wp, self.ch_in),
+            spec_out=f32(B * ns * Fr, LD), frames_out=f32(B * ns * Fr, LD),
+            score=f32(B, ns, T),
+        )
+        self._bufs[key] = b
+        return b
+
+    @contextlib.contextmanager
+    def cached_mixture(self, mix):
+        """Within the context, evaluations with this very ``mix`` tensor (same storage) reuse its
+        spectrogram channel instead of recomputing it; the sampler wraps its loop in this."""
+        prev = (self._mix_cache_on, self._mix_cache)
+        self._mix_cache_on, self._mix_cache = True, None
+        try:
+            yield self
+        finally:
+            self._mix_cache_on, self._mix_cache = prev
+
+    # -------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, xt, time, mix):
+        """xt: [B, n_src, T], time: [B], mix: [B, 1, T] (CUDA fp32) -> score [B, n_src, T]."""
+        if self.backbone is None:
+            raise RuntimeError("ScoreModelNCSNpp has no weights: call load_state_dict first")
+        if xt.dim() != 3 or mix.dim() != 3 or xt.shape[1] != self.num_sources or mix.shape[1] != 1:
+            raise ValueError(f"expected xt [B,{self.num_sources},T] and mix [B,1,T], got {tuple(xt.shape)}, "
+                             f"{tuple(mix.shape)}")
+        B, ns, T = xt.shape
+        if mix.shape[0] != B or mix.shape[2] != T or time.shape != (B,):
+            raise ValueError("xt, time and mix disagree on batch size or length")
+        xt = xt.contiguous().float()
+        mix = mix.contiguous().float()
+        time = time.contiguous().float()
+        bf = self._work(B, T)
+        Fr, Wp = bf["Fr"], bf["Wp"]
+        Ctot = ns + 1
+
+        mix_key = (mix.data_ptr(), B, T)
+        if not (self._mix_cache_on and self._mix_cache == mix_key):
+            ops.stft_frames(mix, self.window, B, 1, T, Fr, bf["frames_mix"])
+            ops.sgemm(bf["frames_mix"], LD, self.basis_fwd, LD, bf["dft_mix"], LD, B * Fr, LD, LD)
+            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, Ctot, 64, self.spec_factor, self.spec_abs_exponent,
+                          bf["x_pyr"], bf["x_planes"])
+            self._mix_cache = mix_key if self._mix_cache_on else None
+        ops.stft_frames(xt, self.window, B, ns, T, Fr, bf["frames"])
+        ops.sgemm(bf["frames"], LD, self.basis_fwd, LD, bf["dft"], LD, B * ns * Fr, LD, LD)
+        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, Ctot, 64, self.spec_factor, self.spec_abs_exponent,
+                      bf["x_pyr"], bf["x_planes"])
+
+        pyr = self.backbone(bf["x_planes"], bf["x_pyr"], time)
+
+        ops.out_head(pyr, B, Wp, self.ch_in, ns, Fr, time, self.backbone.out_w, self.backbone.out_b,
+                     self.spec_factor, self.spec_abs_exponent, bf["spec_out"])
+        ops.sgemm(bf["spec_out"], LD, self.basis_inv, LD, bf["frames_out"], LD, B * ns * Fr, LD, LD)
+        out = torch.empty(B, ns, T, device=self.dev, dtype=torch.float32)
+        ops.istft_ola(bf["frames_out"], self.window, B, ns, Fr, T, out)
+        return out
+
+
+# NCSNpp constructor defaults (reference models/ncsnpp.py:45-70): anything else is not on the hot path
+_BACKBONE_DEFAULTS = dict(
+    scale_by_sigma=True, nonlinearity="swish", ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2,
+    attn_resolutions=(16,), resamp_with_conv=True, conditional=True, fir=True, fir_kernel=[1, 3, 3, 1],
+    skip_rescale=True, resblock_type="biggan", progressive="output_skip", progressive_input="input_skip",
+    progressive_combine="sum", init_scale=0.0, fourier_scale=16, image_size=256, embedding_type="fourier",
+    dropout=0.0, centered=False,
+)

@@ -14,7 +14,7 @@
  * stand in for.  INTEGRATION.md shows the ctypes/pybind stubs a maintainer would add.
  *
  * Layouts: activations are channels-last, fp32 [B, H, W, C]; tensor-core operands are a pair of
- * bf16 planes (hi, lo) with hi + lo == x to 2^-17 ("split" tensors) in the same [B, H, W, C]
+ * fp16 planes (hi, lo) with hi + lo == x to 2^-22 ("split" tensors) in the same [B, H, W, C]
  * layout; waveforms are [B, C, T] fp32.
  */
 #ifndef DSEP_H_
@@ -41,12 +41,14 @@ int dsep_abi_version(void);
 int dsep_device_ok(void);
 
 /* ---- tensor-core convolution -------------------------------------------------------------
- * out[b,h,w,n] = scale * ( sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c] + bias[n] + film[b,n]
- *                          + residual[b,h,w,n] )
+ * out[b,h,w,n] = scale * ( acc_scale * sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c] + bias[n]
+ *                          + film[b,n] + residual[b,h,w,n] )
  * Implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators).  ksize 3 (pad 1) or 1.  A is a split
  * tensor [B,H,W,Cin] (Cin % 64 == 0); Wt a split tensor [ksize*ksize, Cout_pad, Cin] with
  * Cout_pad in {16} or a multiple of 64; only the first cout_store channels are written, with
- * row pitch cout_store.  passes = 3: hi*hi + lo*hi + hi*lo (fp32-grade); passes = 1: hi*hi.
+ * row pitch cout_store.  passes = 3: hi*hi + lo*hi + hi*lo (fp32-grade); passes = 1: hi*hi
+ * (11-bit operands, TF32-grade).  acc_scale undoes the power-of-two pre-scaling that keeps the
+ * fp16 weight planes in the normal range (Wt holds w / acc_scale).
  * bias/film/residual may be NULL.  film is [B, film_stride] (pointer already offset to this
  * layer's first channel).
  * Replaces nn.Conv2d -> cuDNN in ddpm_conv3x3/ddpm_conv1x1 (models/ncsnpp_utils/layers.py:112-156),
@@ -54,10 +56,12 @@ int dsep_device_ok(void);
 int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
                    const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
                    const float* bias, const float* film, int film_stride, const float* residual,
-                   float scale, float* out, int cout_store, int passes, dsep_stream_t stream);
+                   float scale, float acc_scale, float* out, int cout_store, int passes,
+                   dsep_stream_t stream);
 
-/* x (fp32, n elements) -> split bf16 planes. */
-int dsep_split_bf16(const float* x, int64_t n, void* hi, void* lo, dsep_stream_t stream);
+/* x * prescale (fp32, n elements) -> split fp16 planes. */
+int dsep_split_f16(const float* x, int64_t n, float prescale, void* hi, void* lo,
+                   dsep_stream_t stream);
 
 /* ---- GroupNorm / SiLU / FIR resampling ------------------------------------------------------
  * Channel-concatenated input [x0 (C0 ch) | x1 (C1 ch)] (x1 may be NULL, C1 = 0), pixels P=H*W.
@@ -115,8 +119,10 @@ int dsep_film(const float* temb_act, const float* Wd, const float* bd, int B, in
  * Framing exactly as torch.stft(n_fft=510, hop=128, center=True, pad_mode="constant") on the
  * signal right-padded by 382 zeros (score_models.py:107-112): frame f covers samples
  * [128 f - 255, 128 f + 255), zero outside [0,T), times periodic Hann(510).
- * frames: fp32 [B*C*Fr, 512] (columns 510, 511 zero).  x: [B, C, T]. */
-int dsep_stft_frames(const float* x, int B, int C, int T, int Fr, float* frames, dsep_stream_t stream);
+ * frames: fp32 [B*C*Fr, 512] (columns 510, 511 zero).  x: [B, C, T].  window: fp32 [510]
+ * (torch.hann_window(510), the `stft.window` buffer of a checkpoint). */
+int dsep_stft_frames(const float* x, const float* window, int B, int C, int T, int Fr, float* frames,
+                     dsep_stream_t stream);
 /* C[M,N] = A[M,K] * Bm[K,N], fp32 FFMA, row-major, leading dimensions in elements.
  * Used with the DFT-510 basis in place of cuFFT (torch.stft/istft). */
 int dsep_sgemm(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N,
@@ -140,7 +146,8 @@ int dsep_out_head(const float* pyr, int B, int Wp, int Cp, int nsrc, int Fr, con
 /* frames_t [B*C*Fr, 512] (time-domain frames from the inverse basis) -> window, overlap-add,
  * divide by the squared-window envelope, drop 255 samples each side, crop / zero-pad to T
  * (torch.istft; score_models.py:122-123, :99-105).  out [B,C,T]. */
-int dsep_istft_ola(const float* frames_t, int B, int C, int Fr, int T, float* out, dsep_stream_t stream);
+int dsep_istft_ola(const float* frames_t, const float* window, int B, int C, int Fr, int T, float* out,
+                   dsep_stream_t stream);
 
 /* ---- SDE arithmetic -------------------------------------------------------------------------
  * All on x [B,2,T].  t is a device array [B].  sigma_mix [B,T] is NULL for MixSDE and

@@ -1,0 +1,363 @@
+"""GPU parity of every libdsep kernel (through the C-ABI) against the CPU oracle / plain fp32-fp64
+torch restatements of the same op on the same seeded inputs.  Tolerances are written per test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from diffsep_b200 import ops
+    ops.require_device()
+    return ops
+
+
+def cl(x):      # NCHW -> NHWC contiguous on device
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV)
+
+
+def nchw(x):    # NHWC device -> NCHW cpu
+    return x.permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def split(ops, x, prescale=1.0):
+    s = ops.Split.empty(x.shape, DEV)
+    ops.split_f16(x, s, prescale)
+    return s
+
+
+def test_library_loaded_and_device_ok():
+    from diffsep_b200 import _lib
+    lib = _lib.load()
+    assert lib.dsep_abi_version() == 1
+    assert lib.dsep_device_ok() == 1
+
+
+def test_split_f16_reconstructs_fp32():
+    ops = _ops()
+    g = cases.gen(1)
+    x = (torch.randn(4096 * 4, generator=g) * torch.logspace(-4, 2, 4096 * 4)).to(DEV)
+    s = split(ops, x)
+    rec = s.hi.float() + s.lo.float()
+    # 22 significand bits while hi is a normal fp16; 2^-25 absolute below that
+    err = (rec - x).abs()
+    assert bool((err <= 2.0 ** -24 + x.abs() * 2.0 ** -21).all())
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, extras
+    (2, 16, 24, 64, 64, 3, True),
+    (1, 8, 8, 128, 128, 3, False),
+    (3, 4, 4, 256, 256, 3, True),
+    (1, 32, 48, 64, 6, 3, True),
+    (2, 16, 16, 192, 128, 1, True),
+    (1, 40, 20, 128, 384, 1, False),
+    (5, 2, 2, 64, 64, 3, False),
+    (1, 64, 64, 6, 128, 3, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c[:6])))
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_tc(case, passes):
+    """tcgen05 implicit-GEMM conv vs F.conv2d in float64.  passes=3 (hi*hi + lo*hi + hi*lo) must be
+    fp32-grade: rel-L2 < 5e-6 (measured 0.3e-6..3.6e-6; the tensor core's fp32 accumulator truncates,
+    so the error grows with the number of accumulation steps; an fp32 cuDNN/oneDNN conv itself sits
+    at ~1e-7..1e-6 of the fp64 truth); passes=1 is 11-bit operands (TF32-grade): < 1e-3."""
+    ops = _ops()
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, Cin, Cout, k, extras = case
+    g = cases.gen(hash(case) & 0xFFFF)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    cw = ConvWeight(w, bias, DEV)
+    cin_pad = cw.cin_pad
+    xa = torch.zeros(B, H, W, cin_pad)
+    xa[..., :Cin] = x.permute(0, 2, 3, 1)
+    a = split(ops, xa.to(DEV))
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    film = res = None
+    scale = 1.0
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+    if extras:
+        film = torch.randn(B, Cout + 8, generator=g).to(DEV)
+        res = torch.randn(B, H, W, Cout, generator=g).to(DEV)
+        scale = 1.0 / math.sqrt(2.0)
+        ref = (ref + film[:, 4:4 + Cout].cpu().double()[:, :, None, None] + nchw(res).double()) * scale
+        film_v = film[:, 4:] if Cout % 4 == 0 else None
+        if film_v is None:   # narrow path has no alignment constraint, but keep offsets simple
+            film_v = film[:, 4:]
+    ops.conv2d_tc(a, B, H, W, cin_pad, cw.planes, cw.cout_pad, k, out, Cout, bias=cw.bias,
+                  film=film_v if extras else None, film_stride=(Cout + 8) if extras else 0, residual=res,
+                  scale=scale, acc_scale=cw.acc_scale, passes=passes)
+    torch.cuda.synchronize()
+    err = rel_l2(nchw(out), ref)
+    assert err < (5e-6 if passes == 3 else 1e-3), err
+
+
+def test_conv2d_tc_rejects_bad_arguments():
+    ops = _ops()
+    a = ops.Split.zeros((1, 4, 4, 64), DEV)
+    w = ops.Split.zeros((9, 64, 64), DEV)
+    out = torch.empty(1, 4, 4, 64, device=DEV)
+    with pytest.raises(ValueError):
+        ops.conv2d_tc(a, 1, 4, 4, 48, w, 64, 3, out, 64)          # Cin not a multiple of 64
+    with pytest.raises(ValueError):
+        ops.conv2d_tc(a, 1, 4, 4, 64, w, 64, 5, out, 64)          # ksize 5
+    with pytest.raises(ValueError):
+        ops.conv2d_tc(a, 1, 4, 4, 64, w, 64, 3, out, 64, passes=2)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 12, 0), (1, 128, 16, 16, 64), (3, 256, 4, 4, 128), (2, 32, 6, 10, 0)])
+@pytest.mark.parametrize("act", [1, 0])
+def test_groupnorm_silu_split(shape, act):
+    """GN(min(C//4,32) groups, eps 1e-6) [+ SiLU] over a channel-concatenated pair, emitted as split
+    planes, vs F.group_norm in float64: < 1e-6 rel-L2 (fp32 arithmetic on fp64 statistics)."""
+    ops = _ops()
+    B, C0, H, W, C1 = shape
+    g = cases.gen(C0 + C1 + H)
+    x0 = torch.randn(B, C0, H, W, generator=g) * 1.7 + 0.3
+    x1 = torch.randn(B, C1, H, W, generator=g) * 0.6 - 0.2 if C1 else None
+    Ct = C0 + C1
+    gamma = 1 + 0.1 * torch.randn(Ct, generator=g)
+    beta = 0.1 * torch.randn(Ct, generator=g)
+    groups = min(Ct // 4, 32)
+    xcat = torch.cat([x0, x1], 1) if C1 else x0
+    ref = F.group_norm(xcat.double(), groups, gamma.double(), beta.double(), eps=1e-6)
+    if act:
+        ref = ref * torch.sigmoid(ref)
+    d0, d1 = cl(x0), (cl(x1) if C1 else None)
+    stats = torch.empty(B, groups, 2, dtype=torch.float64, device=DEV)
+    ops.gn_stats(d0, C0, d1, C1, B, H * W, groups, stats)
+    a = ops.Split.empty((B, H, W, Ct), DEV)
+    r = ops.Split.empty((B, H, W, Ct), DEV)
+    ops.gn_act_split(d0, C0, d1, C1, B, H * W, groups, stats, gamma.to(DEV), beta.to(DEV), 1e-6, act, a=a, r=r)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(a.hi.float() + a.lo.float()), ref) < 1e-6
+    assert rel_l2(nchw(r.hi.float() + r.lo.float()), xcat) < 1e-6
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fir_resample_matches_reference_golden(golden, mode):
+    """FIR x2 up / down vs the golden produced by the reference's upsample_2d / downsample_2d
+    (tests/golden/make_golden.py): abs err < 1e-6."""
+    ops = _ops()
+    g = golden("fir.npz")
+    x = torch.from_numpy(g["x"])
+    want = torch.from_numpy(g["up" if mode == 1 else "down"])
+    B, C, H, W = x.shape
+    Ho, Wo = want.shape[-2:]
+    y = torch.empty(B, Ho, Wo, C, device=DEV)
+    ops.fir_resample(cl(x), B, H, W, C, mode, y=y)
+    torch.cuda.synchronize()
+    assert float((nchw(y) - want).abs().max()) < 1e-6
+    # the reference's own FFI signature on its own [planes, H, W] layout
+    out = torch.empty(B * C, Ho, Wo, device=DEV)
+    ops.upfirdn2d_planes(x.reshape(B * C, H, W).to(DEV), B * C, H, W, 2 if mode == 1 else 1,
+                         1 if mode == 1 else 2, (2, 1) if mode == 1 else (1, 1), out)
+    torch.cuda.synchronize()
+    assert float((out.cpu().reshape(B, C, Ho, Wo) - want).abs().max()) < 1e-6
+
+
+def test_upfirdn2d_unsupported_mode():
+    ops = _ops()
+    x = torch.zeros(1, 4, 4, device=DEV)
+    with pytest.raises(NotImplementedError):
+        ops.upfirdn2d_planes(x, 1, 4, 4, 3, 1, (1, 1), torch.zeros(1, 12, 12, device=DEV))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fir_fused_groupnorm_branch(mode):
+    """FIR(SiLU(GN(x))) and FIR(x) as split planes (the up/down ResBlock prologue) vs the oracle."""
+    ops = _ops()
+    from oracle import ncsnpp_ref as nr
+    g = cases.gen(40 + mode)
+    B, C, H, W = 2, 64, 8, 12
+    x = torch.randn(B, C, H, W, generator=g)
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    fir = nr.fir_up2 if mode == 1 else nr.fir_down2
+    h = nr.silu(nr.group_norm(x.double(), gamma.double(), beta.double()))
+    ref_a, ref_r = fir(h), fir(x.double())
+    groups = min(C // 4, 32)
+    stats = torch.empty(B, groups, 2, dtype=torch.float64, device=DEV)
+    d = cl(x)
+    ops.gn_stats(d, C, None, 0, B, H * W, groups, stats)
+    Ho, Wo = ref_a.shape[-2:]
+    a = ops.Split.empty((B, Ho, Wo, C), DEV)
+    r = ops.Split.empty((B, Ho, Wo, C), DEV)
+    ops.fir_resample(d, B, H, W, C, mode, groups, stats, gamma.to(DEV), beta.to(DEV), 1e-6, a=a, r=r)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(a.hi.float() + a.lo.float()), ref_a) < 1e-6
+    assert rel_l2(nchw(r.hi.float() + r.lo.float()), ref_r) < 1e-6
+
+
+def test_combine():
+    ops = _ops()
+    g = cases.gen(77)
+    B, P, C, Cp = 2, 96, 128, 6
+    pyr = torch.randn(B, P, Cp, generator=g)
+    h = torch.randn(B, P, C, generator=g)
+    w = torch.randn(C, Cp, generator=g)
+    b = torch.randn(C, generator=g)
+    ref = h.double() + pyr.double() @ w.double().t() + b.double()
+    out = torch.empty(B, P, C, device=DEV)
+    ops.combine(pyr.to(DEV), Cp, w.to(DEV), b.to(DEV), h.to(DEV), out, B, P, C)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref) < 1e-6
+
+
+@pytest.mark.parametrize("S", [16, 256, 120])
+def test_attention(S):
+    ops = _ops()
+    g = cases.gen(S)
+    B, C = 2, 128
+    qkv = torch.randn(B, S, 3 * C, generator=g)
+    q, k, v = qkv.double().split(C, dim=-1)
+    w = torch.softmax(q @ k.transpose(1, 2) * C ** -0.5, dim=-1)
+    ref = w @ v
+    o = ops.Split.empty((B, S, C), DEV)
+    ops.attention(qkv.to(DEV), B, S, C, C ** -0.5, o)
+    torch.cuda.synchronize()
+    assert rel_l2((o.hi.float() + o.lo.float()).cpu(), ref) < 2e-6
+
+
+def test_time_embedding_and_film():
+    ops = _ops()
+    from oracle import ncsnpp_ref as nr, weights as ow
+    params = ow.make_backbone_params(nf=64, seed=0)
+    t = torch.tensor([1.0, 0.5, 0.03, 0.7312])
+    temb = nr.time_embedding({k: v.double() for k, v in params.items()}, t.double())
+    ref = nr.silu(temb)
+    out = torch.empty(4, 256, device=DEV)
+    d = lambda k: params[k].to(DEV)
+    ops.time_embedding(t.to(DEV), d("all_modules.0.W"), d("all_modules.1.weight"), d("all_modules.1.bias"),
+                       d("all_modules.2.weight"), d("all_modules.2.bias"), 4, 64, out)
+    torch.cuda.synchronize()
+    # the fp32 phase log(t)*W*2*pi (~1e2..1e3 rad) carries ~1e-5 absolute rounding, as in the reference
+    assert rel_l2(out.cpu(), ref) < 2e-4
+    ref32 = nr.silu(nr.time_embedding(params, t))
+    assert rel_l2(out.cpu(), ref32) < 2e-4
+    Wd = torch.randn(320, 256, generator=cases.gen(3)) * 0.05
+    bd = torch.randn(320, generator=cases.gen(4))
+    film = torch.empty(4, 320, device=DEV)
+    ops.film(out, Wd.to(DEV), bd.to(DEV), 4, 256, 320, film)
+    torch.cuda.synchronize()
+    assert rel_l2(film.cpu(), out.cpu().double() @ Wd.double().t() + bd.double()) < 1e-6
+
+
+def test_sgemm():
+    ops = _ops()
+    g = cases.gen(5)
+    M, N, K = 300, 512, 512
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    Cm = torch.empty(M, N, device=DEV)
+    ops.sgemm(A.to(DEV), K, Bm.to(DEV), N, Cm, N, M, N, K)
+    torch.cuda.synchronize()
+    assert rel_l2(Cm.cpu(), A.double() @ Bm.double()) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["mix", "priormix"])
+def test_sde_updates(tag):
+    """prior / ald2 corrector / reverse-diffusion predictor kernels vs the oracle closed forms
+    with injected noise: < 2e-6 rel-L2."""
+    ops = _ops()
+    from oracle import sde_ref as sd
+    B, T = 3, 1000
+    g = cases.gen(11)
+    mix = torch.randn(B, 1, T, generator=g)
+    x = torch.randn(B, 2, T, generator=g)
+    score = torch.randn(B, 2, T, generator=g)
+    z = torch.randn(B, 2, T, generator=g)
+    t = torch.tensor([1.0, 0.4, 0.03])
+    p = sd.MixSDEParams(N=30, prior=(tag == "priormix"))
+    sp = ops.sde_params(2.0, 0.05, 0.5)
+    sig = None
+    if p.prior:
+        sig = torch.empty(B, T, device=DEV)
+        ops.sigma_mix(mix.to(DEV), B, T, 510, sig)
+        torch.cuda.synchronize()
+        assert rel_l2(sig.cpu(), sd.sigma_mix(p, mix)[:, 0]) < 1e-6
+    xo = torch.empty(B, 2, T, device=DEV)
+    xm = torch.empty(B, 2, T, device=DEV)
+    ops.sde_prior(sp, mix.to(DEV), sig, z.to(DEV), 0, 0, B, T, xo)
+    torch.cuda.synchronize()
+    assert rel_l2(xo.cpu(), sd.prior_sampling(p, mix, z)) < 2e-6
+    fn = lambda *_: score
+    want_x, want_m = sd.corrector_step(p, fn, x, t, mix, [z], 0.5)
+    ops.sde_corrector(sp, x.to(DEV), score.to(DEV), t.to(DEV), sig, z.to(DEV), 0, 0, 0.5, B, T, xo, xm)
+    torch.cuda.synchronize()
+    assert rel_l2(xo.cpu(), want_x) < 2e-6 and rel_l2(xm.cpu(), want_m) < 2e-6
+    want_x, want_m = sd.predictor_step(p, fn, x, t, mix, z)
+    ops.sde_predictor(sp, x.to(DEV), score.to(DEV), t.to(DEV), sig, z.to(DEV), 0, 0, 1.0 / 30, B, T, xo, xm)
+    torch.cuda.synchronize()
+    assert rel_l2(xo.cpu(), want_x) < 2e-6 and rel_l2(xm.cpu(), want_m) < 2e-6
+
+
+def test_sde_unaligned_length_uses_scalar_path():
+    ops = _ops()
+    from oracle import sde_ref as sd
+    B, T = 2, 1001
+    g = cases.gen(12)
+    mix, x, score, z = (torch.randn(B, c, T, generator=g) for c in (1, 2, 2, 2))
+    t = torch.tensor([0.9, 0.2])
+    p = sd.MixSDEParams(N=10)
+    want_x, _ = sd.predictor_step(p, lambda *_: score, x, t, mix, z)
+    xo = torch.empty(B, 2, T, device=DEV)
+    ops.sde_predictor(ops.sde_params(2.0, 0.05, 0.5), x.to(DEV), score.to(DEV), t.to(DEV), None, z.to(DEV), 0, 0,
+                      0.1, B, T, xo, None)
+    torch.cuda.synchronize()
+    assert rel_l2(xo.cpu(), want_x) < 2e-6
+
+
+def test_in_kernel_noise_is_standard_normal_and_reproducible():
+    ops = _ops()
+    n = 1 << 22
+    z = torch.empty(n, device=DEV)
+    ops.randn(z, 1234, 7)
+    z2 = torch.empty(n, device=DEV)
+    ops.randn(z2, 1234, 7)
+    z3 = torch.empty(n, device=DEV)
+    ops.randn(z3, 1234, 8)
+    torch.cuda.synchronize()
+    assert torch.equal(z, z2) and not torch.equal(z, z3)
+    assert abs(float(z.mean())) < 3e-3 and abs(float(z.std()) - 1) < 3e-3
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.05
+    assert abs(float((z * z3).mean())) < 3e-3
+    # the fused prior kernel draws the same stream: x = 0.5 mix + L z with mix = 0
+    B, T = 2, 4096
+    x = torch.empty(B, 2, T, device=DEV)
+    ops.sde_prior(ops.sde_params(2.0, 0.05, 0.5), torch.zeros(B, 1, T, device=DEV), None, None, 99, 3, B, T, x)
+    zz = torch.empty(B, 2, T, device=DEV)
+    ops.randn(zz, 99, 3)
+    x_inj = torch.empty(B, 2, T, device=DEV)
+    ops.sde_prior(ops.sde_params(2.0, 0.05, 0.5), torch.zeros(B, 1, T, device=DEV), None, zz, 0, 0, B, T, x_inj)
+    torch.cuda.synchronize()
+    assert torch.allclose(x, x_inj, rtol=0, atol=0)
+
+
+def test_normalize_and_scale_output(golden):
+    ops = _ops()
+    g = golden("misc.npz")
+    m = cases.batch_mix(3, 512) * 3.0 + 0.2
+    out = torch.empty(3, 1, 512, device=DEV)
+    mean = torch.empty(3, device=DEV)
+    std = torch.empty(3, device=DEV)
+    ops.normalize(m.to(DEV), 3, 512, out, mean, std)
+    sep = torch.randn(3, 2, 512, generator=cases.gen(5))
+    sc = torch.empty(3, 2, 512, device=DEV)
+    ops.scale_output(m.to(DEV), sep.to(DEV), 3, 2, 512, sc)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), g["norm"]) < 1e-6
+    assert rel_l2(sc.cpu(), g["scaled"]) < 1e-6
