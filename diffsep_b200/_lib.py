@@ -89,5 +89,10 @@ def check(rc: int, name: str = "dsep"):
     raise RuntimeError(f"{name}: {msg} (code {rc})")
 
 
+N_CALLS = 0   # C-ABI calls made so far; each launches one kernel (bench.py reports the count)
+
+
 def call(name: str, *args):
+    global N_CALLS
+    N_CALLS += 1
     check(getattr(load(), name)(*args), name)

@@ -1,0 +1,170 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dsep.h declares (no compute
+calls), host-side plugin logic (registries, time grids, noise injection, config handling), and the
+world-size-2 sharding path over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from diffsep_b200 import build
+    build.build()
+    from diffsep_b200 import _lib
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from diffsep_b200 import _lib
+    header = (ROOT / "include" / "dsep.h").read_text()
+    declared = set(re.findall(r"\b(dsep_[a-z0-9_]+)\s*\(", header)) - {"dsep_stream_t"}
+    assert len(declared) >= 26
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS)
+    assert lib.dsep_abi_version() == 1
+
+
+def test_abi_argument_counts_match_header():
+    from diffsep_b200 import _lib
+    header = (ROOT / "include" / "dsep.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for name, argtypes in _lib.PROTOTYPES.items():
+        m = re.search(r"\bint\s+" + name + r"\s*\((.*?)\)\s*;", header, flags=re.S)
+        assert m, name
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(argtypes), name
+
+
+def test_no_fallback_without_gpu(lib):
+    """The product path fails loudly instead of falling back when there is no device."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from diffsep_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.require_device()
+    from diffsep_b200.score_model import ScoreModelNCSNpp
+    with pytest.raises(RuntimeError):
+        ScoreModelNCSNpp(num_sources=2, backbone_args=dict(nf=64))
+    with pytest.raises(ValueError):
+        ops.ptr(torch.zeros(4))       # CPU tensors are rejected, never computed on
+
+
+def test_product_does_not_import_oracle():
+    bad = []
+    for p in list((ROOT / "diffsep_b200").rglob("*.py")) + [ROOT / "separate.py"]:
+        if re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), flags=re.M):
+            bad.append(str(p))
+    assert not bad, bad
+
+
+def test_synthetic_weights_match_oracle_copy():
+    from diffsep_b200 import synthetic
+    from oracle import weights as ow
+    a = synthetic.make_score_model_state_dict(nf=32, seed=3)
+    b = ow.make_score_model_state_dict(nf=32, seed=3)
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_registries_and_errors():
+    from diffsep_b200 import sdes
+    assert set(sdes.PredictorRegistry.get_all_names()) == {"euler_maruyama", "reverse_diffusion", "none"}
+    assert set(sdes.CorrectorRegistry.get_all_names()) == {"ald2", "none"}
+    assert set(sdes.SDERegistry.get_all_names()) == {"mix", "priormix"}
+    with pytest.raises(ValueError, match="unknown"):
+        sdes.PredictorRegistry.get_by_name("heun")
+    with pytest.warns(UserWarning, match="doubly registered"):
+        @sdes.PredictorRegistry.register("none")
+        class Again(sdes.predictors.NonePredictor):
+            pass
+    sde = sdes.MixSDE(ndim=2, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5, N=30)
+    c = sde.copy()
+    c.N = 5
+    assert sde.N == 30 and c.N == 5 and c.T == 1.0
+    with pytest.raises(NotImplementedError):
+        sdes.MixSDE(ndim=3, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5)
+    class OtherSDE(sdes.SDE):
+        pass
+    with pytest.raises(NotImplementedError, match="not yet supported"):
+        sdes.correctors.AnnealedLangevinDynamics2(OtherSDE(2, 2.0, 0.05, 0.5), None, 0.5, 1)
+
+
+def test_time_grids_match_oracle():
+    from diffsep_b200 import sdes
+    from oracle import sde_ref as sd
+    sde = sdes.MixSDE(2, 2.0, 0.05, 0.5, N=30)
+    p = sd.MixSDEParams(N=30)
+    for sched in (None, "linear", "log", "revlog"):
+        assert torch.equal(sdes._timesteps(sde, 0.03, sched, "cpu"), sd.timesteps(p, 0.03, sched))
+    with pytest.raises(NotImplementedError):
+        sdes._timesteps(sde, 0.03, "fib", "cpu")
+
+
+def test_noise_injection_order_and_exhaustion():
+    from diffsep_b200.sdes import noise
+    zs = [torch.full((1, 2, 4), float(i)) for i in range(2)]
+    with noise.injected_noise(zs):
+        a, _, _ = noise.SOURCE.next((1, 2, 4), "cpu")
+        b, _, _ = noise.SOURCE.next((1, 2, 4), "cpu")
+        assert float(a[0, 0, 0]) == 0.0 and float(b[0, 0, 0]) == 1.0
+        with pytest.raises(RuntimeError):
+            noise.SOURCE.next((1, 2, 4), "cpu")
+    z, seed, off = noise.SOURCE.next((1, 2, 4), "cpu")
+    assert z is None and off > 0
+    with noise.injected_noise([torch.zeros(1, 2, 5)]):
+        with pytest.raises(ValueError):
+            noise.SOURCE.next((1, 2, 4), "cpu")
+
+
+def test_shard_bounds_cover_batch_exactly():
+    from diffsep_b200.shard import shard_bounds
+    for n in (0, 1, 7, 32, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) <= -(-n // world) if n else True
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DSEP_ROOT"])
+from diffsep_b200.shard import shard_bounds, gather_estimates
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+for n in (5, 4, 1):
+    full = torch.arange(n * 2 * 3, dtype=torch.float32).reshape(n, 2, 3)
+    lo, hi = shard_bounds(n, rank, world)
+    local = full[lo:hi] * 2.0            # stand-in for the per-shard separation
+    out = gather_estimates(local, n)
+    assert out.shape == full.shape and torch.equal(out, full * 2.0), (rank, n)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, DSEP_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+def test_config_handling_without_hydra():
+    from diffsep_b200.pl_model import DEFAULT_CONFIG, _ns, _to_plain
+    ns = _ns(DEFAULT_CONFIG)
+    assert ns.model.sampler.N == 30 and ns.model.fs == 8000
+    assert _to_plain(ns) == DEFAULT_CONFIG

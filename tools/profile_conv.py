@@ -1,0 +1,51 @@
+"""Runs the dominant kernel alone — the level-0 ResBlock 3x3 convolution (128 -> 128 channels,
+256x256 map, batch 32) — for `ncu --set full`, and prints its CUDA-event time.
+
+    ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 3 -c 2 \
+        -o gpurun_out/conv python tools/profile_conv.py
+"""
+import math
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+from diffsep_b200 import ops  # noqa: E402
+from diffsep_b200.backbone import ConvWeight  # noqa: E402
+
+B = int(os.environ.get("DSEP_BENCH_BATCH", "32"))
+H = W = int(os.environ.get("DSEP_HW", "256"))
+CIN = int(os.environ.get("DSEP_CIN", "128"))
+COUT = int(os.environ.get("DSEP_COUT", "128"))
+K = int(os.environ.get("DSEP_K", "3"))
+passes = int(os.environ.get("DSEP_PASSES", "3"))
+with_res = int(os.environ.get("DSEP_RES", "0"))
+reps = int(os.environ.get("DSEP_REPS", "5"))
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+w = torch.randn(COUT, CIN, K, K, generator=g) / math.sqrt(CIN * K * K)
+cw = ConvWeight(w, torch.zeros(COUT), dev)
+x = torch.randn(B, H, W, CIN, device=dev)
+a = ops.Split.empty((B, H, W, CIN), dev)
+ops.split_f16(x, a)
+out = torch.empty(B, H, W, COUT, device=dev)
+res = torch.randn(B, H, W, COUT, device=dev) if with_res else None
+run = lambda: ops.conv2d_tc(a, B, H, W, CIN, cw.planes, cw.cout_pad, K, out, COUT, bias=cw.bias, residual=res,
+                            scale=0.7071 if with_res else 1.0, acc_scale=cw.acc_scale, passes=passes)
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    run()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+fl = 2.0 * B * H * W * K * K * CIN * COUT
+print(f"conv {K}x{K} {CIN}->{COUT} {H}x{W} B={B} passes={passes} res={with_res}: {ms:.3f} ms  "
+      f"{fl / ms / 1e9:.1f} TFLOP/s algorithmic, {passes * fl / ms / 1e9:.1f} TFLOP/s issued", flush=True)
