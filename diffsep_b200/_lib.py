@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libdsep.so"
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -25,10 +25,12 @@ class SdeParams(C.Structure):
 
 # name -> argument types, exactly the prototypes of include/dsep.h (return type int)
 PROTOTYPES = {
-    "dsep_conv2d_tc": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _f, _f, _p, _i, _i, _p],
+    "dsep_conv2d_tc": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _p, _p, _i, _p, _f, _f, _p, _i,
+                       _p, _i, _p],
     "dsep_split_f16": [_p, _i64, _f, _p, _p, _p],
-    "dsep_gn_stats": [_p, _i, _p, _i, _i, _i, _i, _p, _p],
-    "dsep_gn_act_split": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p],
+    "dsep_channel_stats": [_p, _i, _i, _i, _p, _p],
+    "dsep_zero": [_p, _i64, _p],
+    "dsep_gn_act_split": [_p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p, _p],
     "dsep_fir_resample": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
     "dsep_upfirdn2d": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "dsep_combine": [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p],
@@ -92,7 +94,16 @@ def check(rc: int, name: str = "dsep"):
 N_CALLS = 0   # C-ABI calls made so far; each launches one kernel (bench.py reports the count)
 
 
+_DEBUG_SYNC = bool(int(__import__("os").environ.get("DSEP_DEBUG_SYNC", "0")))
+
+
 def call(name: str, *args):
     global N_CALLS
     N_CALLS += 1
     check(getattr(load(), name)(*args), name)
+    if _DEBUG_SYNC:   # debugging aid: attribute an asynchronous CUDA error to the call that caused it
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise RuntimeError(f"{name}{args}: {e}") from e

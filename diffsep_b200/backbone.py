@@ -41,10 +41,18 @@ def gn_groups(c):
     return min(c // 4, 32)
 
 
-class ConvWeight:
-    """Tensor-core weight: split fp16 planes [taps, Cout_pad, Cin_pad] + fp32 bias."""
+def _prescale_exp(amax):
+    """power of two k with amax * 2^k in [1024, 2048): both fp16 planes of a weight stay normal."""
+    return 0 if amax == 0.0 else 10 - math.floor(math.log2(amax))
 
-    def __init__(self, w_oihw, bias, device):
+
+class ConvWeight:
+    """Tensor-core weight: split fp16 planes [taps, Cout_pad, Cin_pad] + fp32 bias.
+
+    ``shortcut`` (a 1x1 ConvWeight source: weight, bias) is folded in as the fused second operand of
+    ``dsep_conv2d_tc``: both weights share one power-of-two pre-scale and the biases are summed."""
+
+    def __init__(self, w_oihw, bias, device, shortcut=None):
         w = w_oihw.detach().to(device=device, dtype=torch.float32)
         cout, cin, kh, kw = w.shape
         assert kh == kw and kh in (1, 3)
@@ -53,16 +61,33 @@ class ConvWeight:
         self.cout_pad = 16 if cout <= 16 else _round_up(cout, 64)
         wt = torch.zeros(kh * kw, self.cout_pad, self.cin_pad, device=device, dtype=torch.float32)
         wt[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
-        # power-of-two pre-scale: largest |w| lands in [1024, 2048) so both fp16 planes stay normal
         amax = float(wt.abs().max())
-        k = 0 if amax == 0.0 else 10 - math.floor(math.log2(amax))
+        w2t = None
+        if shortcut is not None:
+            w2 = shortcut[0].detach().to(device=device, dtype=torch.float32)
+            assert w2.shape[0] == cout and w2.shape[2:] == (1, 1)
+            self.cin2 = w2.shape[1]
+            self.cin2_pad = _round_up(self.cin2, 64)
+            w2t = torch.zeros(self.cout_pad, self.cin2_pad, device=device, dtype=torch.float32)
+            w2t[:cout, :self.cin2] = w2.reshape(cout, self.cin2)
+            amax = max(amax, float(w2t.abs().max()))
+        else:
+            self.cin2 = self.cin2_pad = 0
+        k = _prescale_exp(amax)
         self.acc_scale = 2.0 ** (-k)
         self.planes = Split.empty(wt.shape, device)
         ops.split_f16(wt, self.planes, prescale=2.0 ** k)
+        self.planes2 = None
+        if w2t is not None:
+            self.planes2 = Split.empty(w2t.shape, device)
+            ops.split_f16(w2t, self.planes2, prescale=2.0 ** k)
         self.bias = None
-        if bias is not None:
+        if bias is not None or (shortcut is not None and shortcut[1] is not None):
             b = torch.zeros(self.cout_pad, device=device, dtype=torch.float32)
-            b[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+            if bias is not None:
+                b[:cout] += bias.detach().to(device=device, dtype=torch.float32)
+            if shortcut is not None and shortcut[1] is not None:
+                b[:cout] += shortcut[1].detach().to(device=device, dtype=torch.float32)
             self.bias = b
 
 
@@ -153,10 +178,11 @@ class NCSNppB200:
             rb["gn0"] = (f32(mod(i, "GroupNorm_0.weight")), f32(mod(i, "GroupNorm_0.bias")))
             rb["gn1"] = (f32(mod(i, "GroupNorm_1.weight")), f32(mod(i, "GroupNorm_1.bias")))
             rb["conv0"] = ConvWeight(P[mod(i, "Conv_0.weight")], P[mod(i, "Conv_0.bias")], dev)
-            rb["conv1"] = ConvWeight(P[mod(i, "Conv_1.weight")], P[mod(i, "Conv_1.bias")], dev)
-            rb["conv2"] = None
-            if mod(i, "Conv_2.weight") in P:
-                rb["conv2"] = ConvWeight(P[mod(i, "Conv_2.weight")], P[mod(i, "Conv_2.bias")], dev)
+            shortcut = None
+            if mod(i, "Conv_2.weight") in P:     # 1x1 shortcut: fused into Conv_1's accumulation
+                shortcut = (P[mod(i, "Conv_2.weight")], P[mod(i, "Conv_2.bias")])
+            rb["conv1"] = ConvWeight(P[mod(i, "Conv_1.weight")], P[mod(i, "Conv_1.bias")], dev, shortcut=shortcut)
+            rb["has_shortcut"] = shortcut is not None
             rb["film_off"] = self._film_rows
             dense_w.append(f32(mod(i, "Dense_0.weight")))
             dense_b.append(f32(mod(i, "Dense_0.bias")))
@@ -232,7 +258,30 @@ class NCSNppB200:
         return self.plan(B, W).run(x_planes, x_pyramid, t)
 
 
+class Act:
+    """An fp32 activation [B, H, W, C] plus (once known) its per-channel GroupNorm sums [B, C, 2]."""
+
+    __slots__ = ("t", "C", "H", "W", "st")
+
+    def __init__(self, t, C, H, W, st=None):
+        self.t, self.C, self.H, self.W, self.st = t, C, H, W, st
+
+
+def _tile_has_one_batch_entry(H, W):
+    """mirrors the 128-pixel tile choice of dsep_conv2d_tc: fused statistics need tb == 1"""
+    def p2(v):
+        l = 1
+        while l < v:
+            l *= 2
+        return l
+    tw = min(16, p2(W))
+    th = min(128 // tw, p2(H))
+    return tw * th == 128
+
+
 class _Plan:
+    STATS_CHUNK = 8 << 20
+
     def __init__(self, net: NCSNppB200, B, W):
         self.net, self.B, self.W = net, B, W
         self.steps = []          # list of zero-arg callables
@@ -240,83 +289,104 @@ class _Plan:
         dev = net.device
         self.temb_act = torch.empty(B, net.temb_dim, device=dev, dtype=torch.float32)
         self.film = torch.empty(B, net._film_rows, device=dev, dtype=torch.float32)
-        self.t_in = torch.empty(B, device=dev, dtype=torch.float32)
         self.x_planes = None     # bound at run time
         self.x_pyramid = None
+        self._stat_chunks, self._stat_used = [], self.STATS_CHUNK
         self._build()
 
+    # -- GroupNorm statistics slots (zeroed once per evaluation, never recycled within one) ----------
+    def _slot(self, C):
+        n = self.B * C * 2
+        if self._stat_used + n * 8 > self.STATS_CHUNK:
+            self._stat_chunks.append(torch.empty(max(self.STATS_CHUNK, n * 8) // 8, device=self.net.device,
+                                                 dtype=torch.float64))
+            self._stat_used = 0
+        off = self._stat_used // 8
+        self._stat_used += _round_up(n * 8, 256)
+        return self._stat_chunks[-1][off:off + n].view(self.B, C, 2)
+
+    def _ensure_stats(self, x: Act):
+        if x.st is None:
+            x.st = self._slot(x.C)
+            t, C, P, st, B = x.t, x.C, x.H * x.W, x.st, self.B
+            self.steps.append(lambda: ops.channel_stats(t, C, B, P, st))
+        return x.st
+
+    def _fused_slot(self, H, W, C):
+        return self._slot(C) if (C >= 64 and _tile_has_one_batch_entry(H, W)) else None
+
     # -- helpers that append launches ------------------------------------------------------
-    def _conv(self, a, H, W, cin_pad, cw: ConvWeight, out, cout_store, film=None, residual=None, scale=1.0):
+    def _conv(self, a, H, W, cin_pad, cw: ConvWeight, out, cout_store, film=None, residual=None, scale=1.0,
+              a2=None, stats=None):
         net, B = self.net, self.B
         film_v, stride = None, 0
         if film is not None:
             film_v, stride = self.film[:, film:], self.film.shape[1]
+        w2 = cw.planes2 if a2 is not None else None
+        cin2 = cw.cin2_pad if a2 is not None else 0
         self.steps.append(lambda: ops.conv2d_tc(
             a() if callable(a) else a, B, H, W, cin_pad, cw.planes, cw.cout_pad, cw.ksize, out, cout_store,
             bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
-            acc_scale=cw.acc_scale, passes=net.passes))
+            acc_scale=cw.acc_scale, passes=net.passes, a2=a2, Cin2=cin2, w2=w2, stats=stats))
 
-    def _resblock(self, rb, x0, C0, x1, C1, H, W, mode=0):
-        """mode 0 plain, 1 up, 2 down.  Returns (out, Ho, Wo)."""
+    def _resblock(self, rb, x: Act, skip: Act = None, mode=0, want_stats=True) -> Act:
+        """ResnetBlockBigGANpp (layerspp.py:291-323).  mode 0 plain, 1 up, 2 down."""
         ar, B = self.arena, self.B
-        Cin, Cout = C0 + C1, rb["cout"]
+        C0, C1 = x.C, (skip.C if skip is not None else 0)
+        Cin, Cout, H, W = C0 + C1, rb["cout"], x.H, x.W
         assert Cin == rb["cin"], (Cin, rb["cin"])
         g0 = gn_groups(Cin)
-        stats0 = ar.f64(B, g0, 2)
-        self.steps.append(lambda: ops.gn_stats(x0, C0, x1, C1, B, H * W, g0, stats0))
+        st0 = self._ensure_stats(x)
+        st1 = self._ensure_stats(skip) if skip is not None else None
+        x0, x1 = x.t, (skip.t if skip is not None else None)
         Ho, Wo = (H * 2, W * 2) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
         a = ar.split(B, Ho, Wo, Cin)
-        r = ar.split(B, Ho, Wo, Cin) if rb["conv2"] is not None else None
+        r = ar.split(B, Ho, Wo, Cin) if rb["has_shortcut"] else None
         gam0, bet0 = rb["gn0"]
         if mode == 0:
-            self.steps.append(lambda: ops.gn_act_split(x0, C0, x1, C1, B, H * W, g0, stats0, gam0, bet0, GN_EPS,
+            self.steps.append(lambda: ops.gn_act_split(x0, C0, st0, x1, C1, st1, B, H * W, g0, gam0, bet0, GN_EPS,
                                                        1, a=a, r=r))
         else:
             assert x1 is None and r is not None
-            self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, stats0, gam0, bet0, GN_EPS,
+            self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
                                                        a=a, r=r))
-        h = ar.f32(B, Ho, Wo, Cout)
-        self._conv(a, Ho, Wo, Cin, rb["conv0"], h, Cout, film=rb["film_off"])
+        h = Act(ar.f32(B, Ho, Wo, Cout), Cout, Ho, Wo, self._fused_slot(Ho, Wo, Cout))
+        self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st)
         ar.release(a)
-        ar.release(stats0)
         g1 = gn_groups(Cout)
-        stats1 = ar.f64(B, g1, 2)
-        self.steps.append(lambda: ops.gn_stats(h, Cout, None, 0, B, Ho * Wo, g1, stats1))
+        st_h = self._ensure_stats(h)
         a2 = ar.split(B, Ho, Wo, Cout)
         gam1, bet1 = rb["gn1"]
-        self.steps.append(lambda: ops.gn_act_split(h, Cout, None, 0, B, Ho * Wo, g1, stats1, gam1, bet1, GN_EPS,
-                                                   1, a=a2))
-        ar.release(stats1)
-        if rb["conv2"] is not None:
-            xs = ar.f32(B, Ho, Wo, Cout)
-            self._conv(r, Ho, Wo, Cin, rb["conv2"], xs, Cout)
+        ht = h.t
+        self.steps.append(lambda: ops.gn_act_split(ht, Cout, st_h, None, 0, None, B, Ho * Wo, g1, gam1, bet1,
+                                                   GN_EPS, 1, a=a2))
+        # conv1 never reads h (only a2), so its buffer is reused for the block output
+        out = Act(h.t, Cout, Ho, Wo, self._fused_slot(Ho, Wo, Cout) if want_stats else None)
+        if rb["has_shortcut"]:
+            self._conv(a2, Ho, Wo, Cout, rb["conv1"], out.t, Cout, scale=INV_SQRT2, a2=r, stats=out.st)
             ar.release(r)
         else:
-            assert x1 is None and Cin == Cout
-            xs = x0
-        out = h   # conv1 never reads h (only a2), so its buffer is reused for the block output
-        self._conv(a2, Ho, Wo, Cout, rb["conv1"], out, Cout, residual=xs, scale=INV_SQRT2)
+            assert x1 is None and Cin == Cout and mode == 0
+            self._conv(a2, Ho, Wo, Cout, rb["conv1"], out.t, Cout, residual=x0, scale=INV_SQRT2, stats=out.st)
         ar.release(a2)
-        if rb["conv2"] is not None:
-            ar.release(xs)
-        return out, Ho, Wo
+        return out
 
-    def _attn(self, at, x, H, W):
-        ar, B, Cc = self.arena, self.B, at["c"]
+    def _attn(self, at, x: Act) -> Act:
+        """AttnBlockpp (layerspp.py:76-92)."""
+        ar, B, Cc, H, W = self.arena, self.B, at["c"], x.H, x.W
         S = H * W
         g = gn_groups(Cc)
-        stats = ar.f64(B, g, 2)
-        self.steps.append(lambda: ops.gn_stats(x, Cc, None, 0, B, S, g, stats))
+        st = self._ensure_stats(x)
         a = ar.split(B, H, W, Cc)
         gam, bet = at["gn"]
-        self.steps.append(lambda: ops.gn_act_split(x, Cc, None, 0, B, S, g, stats, gam, bet, GN_EPS, 0, a=a))
-        ar.release(stats)
+        xt = x.t
+        self.steps.append(lambda: ops.gn_act_split(xt, Cc, st, None, 0, None, B, S, g, gam, bet, GN_EPS, 0, a=a))
         qkv = ar.f32(B, S, 3 * Cc)
         self._conv(a, H, W, Cc, at["qkv"], qkv, 3 * Cc)
         o = a   # the GN'd input planes are dead once q, k, v exist
         self.steps.append(lambda: ops.attention(qkv, B, S, Cc, float(Cc) ** -0.5, o))
-        out = ar.f32(B, H, W, Cc)
-        self._conv(o, H, W, Cc, at["proj"], out, Cc, residual=x, scale=INV_SQRT2)
+        out = Act(ar.f32(B, H, W, Cc), Cc, H, W, self._fused_slot(H, W, Cc))
+        self._conv(o, H, W, Cc, at["proj"], out.t, Cc, residual=xt, scale=INV_SQRT2, stats=out.st)
         ar.release(o)
         ar.release(qkv)
         return out
@@ -325,97 +395,90 @@ class _Plan:
         net, ar, B, W0 = self.net, self.arena, self.B, self.W
         nf, ch_in = net.nf, net.ch_in
         nres = len(CH_MULT)
-        # refcounts for skip tensors: released after their last consumer
         H, W = 256, W0
-        h = ar.f32(B, H, W, nf)
-        self._conv(lambda: self.x_planes, H, W, net.conv_in.cin_pad, net.conv_in, h, nf)
-        hs = [(h, nf)]
+        h = Act(ar.f32(B, H, W, nf), nf, H, W, self._fused_slot(H, W, nf))
+        self._conv(lambda: self.x_planes, H, W, net.conv_in.cin_pad, net.conv_in, h.t, nf, stats=h.st)
+        hs = [h]
         pyr_in = None            # running input pyramid (fp32, ch_in channels); level 0 = x_pyramid
-        cur_c = nf
         for lvl, level in enumerate(net.down):
             for rb, at in zip(level["blocks"], level["attn"]):
-                x_prev, c_prev = hs[-1]
-                h, _, _ = self._resblock(rb, x_prev, c_prev, None, 0, H, W)
-                cur_c = rb["cout"]
+                h = self._resblock(rb, hs[-1])
                 if at is not None:
-                    h2 = self._attn(at, h, H, W)
-                    ar.release(h)
+                    h2 = self._attn(at, h)
+                    ar.release(h.t)
                     h = h2
-                hs.append((h, cur_c))
+                hs.append(h)
             if lvl != nres - 1:
-                x_prev, c_prev = hs[-1]
-                h, Hn, Wn = self._resblock(level["down"], x_prev, c_prev, None, 0, H, W, mode=2)
-                new_pyr = ar.f32(B, Hn, Wn, ch_in)
+                # the Combine below rewrites h in place, so its statistics are taken afterwards
+                h = self._resblock(level["down"], hs[-1], mode=2, want_stats=False)
+                new_pyr = ar.f32(B, h.H, h.W, ch_in)
                 src = pyr_in
-                Hc, Wc = H, W
                 if src is None:
-                    self.steps.append(lambda Hc=Hc, Wc=Wc, new_pyr=new_pyr: ops.fir_resample(
+                    self.steps.append(lambda Hc=H, Wc=W, new_pyr=new_pyr: ops.fir_resample(
                         self.x_pyramid, B, Hc, Wc, ch_in, 2, y=new_pyr))
                 else:
-                    self.steps.append(lambda src=src, Hc=Hc, Wc=Wc, new_pyr=new_pyr: ops.fir_resample(
+                    self.steps.append(lambda src=src, Hc=H, Wc=W, new_pyr=new_pyr: ops.fir_resample(
                         src, B, Hc, Wc, ch_in, 2, y=new_pyr))
                     ar.release(src)
                 pyr_in = new_pyr
                 cw, cb = level["combine"]
-                self.steps.append(lambda pyr=new_pyr, cw=cw, cb=cb, h=h, P=Hn * Wn, c=cur_c: ops.combine(
-                    pyr, ch_in, cw, cb, h, h, B, P, c))
-                H, W = Hn, Wn
-                hs.append((h, cur_c))
+                self.steps.append(lambda pyr=new_pyr, cw=cw, cb=cb, t=h.t, P=h.H * h.W, c=h.C: ops.combine(
+                    pyr, ch_in, cw, cb, t, t, B, P, c))
+                H, W = h.H, h.W
+                hs.append(h)
         if pyr_in is not None:
             ar.release(pyr_in)
 
-        h, cur_c = hs[-1]
-        h_mid, _, _ = self._resblock(net.mid[0], h, cur_c, None, 0, H, W)
-        h2 = self._attn(net.mid[1], h_mid, H, W)
-        ar.release(h_mid)
-        h3, _, _ = self._resblock(net.mid[2], h2, cur_c, None, 0, H, W)
-        ar.release(h2)
-        h = h3
+        h_mid = self._resblock(net.mid[0], hs[-1])
+        h2 = self._attn(net.mid[1], h_mid)
+        ar.release(h_mid.t)
+        h = self._resblock(net.mid[2], h2)
+        ar.release(h2.t)
 
         pyramid = None
         for level in net.up:
             for rb in level["blocks"]:
-                skip, c_skip = hs.pop()
-                h_new, _, _ = self._resblock(rb, h, cur_c, skip, c_skip, H, W)
-                ar.release(h)
-                ar.release(skip)
-                h, cur_c = h_new, rb["cout"]
+                skip = hs.pop()
+                h_new = self._resblock(rb, h, skip)
+                ar.release(h.t)
+                ar.release(skip.t)
+                h = h_new
             if level["attn"] is not None:
-                h2 = self._attn(level["attn"], h, H, W)
-                ar.release(h)
+                h2 = self._attn(level["attn"], h)
+                ar.release(h.t)
                 h = h2
             # output pyramid: conv3x3(SiLU(GN(h))) (+ FIR-up of the running pyramid), ncsnpp.py:419-440
-            g = gn_groups(cur_c)
-            stats = ar.f64(B, g, 2)
-            self.steps.append(lambda h=h, c=cur_c, P=H * W, g=g, stats=stats: ops.gn_stats(h, c, None, 0, B, P, g, stats))
-            a = ar.split(B, H, W, cur_c)
+            g = gn_groups(h.C)
+            st = self._ensure_stats(h)
+            a = ar.split(B, h.H, h.W, h.C)
             gam, bet = level["pyr_gn"]
-            self.steps.append(lambda h=h, c=cur_c, P=H * W, g=g, stats=stats, gam=gam, bet=bet, a=a:
-                              ops.gn_act_split(h, c, None, 0, B, P, g, stats, gam, bet, GN_EPS, 1, a=a))
-            ar.release(stats)
-            new_pyr = ar.f32(B, H, W, ch_in)
+            self.steps.append(lambda t=h.t, c=h.C, P=h.H * h.W, g=g, st=st, gam=gam, bet=bet, a=a:
+                              ops.gn_act_split(t, c, st, None, 0, None, B, P, g, gam, bet, GN_EPS, 1, a=a))
+            new_pyr = ar.f32(B, h.H, h.W, ch_in)
             up = None
             if pyramid is not None:
-                up = ar.f32(B, H, W, ch_in)
-                self.steps.append(lambda src=pyramid, Hs=H // 2, Ws=W // 2, up=up: ops.fir_resample(
+                up = ar.f32(B, h.H, h.W, ch_in)
+                self.steps.append(lambda src=pyramid, Hs=h.H // 2, Ws=h.W // 2, up=up: ops.fir_resample(
                     src, B, Hs, Ws, ch_in, 1, y=up))
                 ar.release(pyramid)
-            self._conv(a, H, W, cur_c, level["pyr_conv"], new_pyr, ch_in, residual=up)
+            self._conv(a, h.H, h.W, h.C, level["pyr_conv"], new_pyr, ch_in, residual=up)
             ar.release(a)
             if up is not None:
                 ar.release(up)
             pyramid = new_pyr
             if level["up"] is not None:
-                h_new, H, W = self._resblock(level["up"], h, cur_c, None, 0, H, W, mode=1)
-                ar.release(h)
+                h_new = self._resblock(level["up"], h, mode=1)
+                ar.release(h.t)
                 h = h_new
-        assert not hs and H == 256 and W == W0
-        ar.release(h)
+        assert not hs and h.H == 256 and h.W == W0
+        ar.release(h.t)
         self.out = pyramid
 
     def run(self, x_planes, x_pyramid, t):
         net, B = self.net, self.B
         self.x_planes, self.x_pyramid = x_planes, x_pyramid
+        for chunk in self._stat_chunks:
+            ops.zero(chunk)
         ops.time_embedding(t, net.Wf, net.t_w1, net.t_b1, net.t_w2, net.t_b2, B, net.nf, self.temb_act)
         ops.film(self.temb_act, net.dense_w, net.dense_b, B, net.temb_dim, net._film_rows, self.film)
         for step in self.steps:

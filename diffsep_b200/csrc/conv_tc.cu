@@ -1,25 +1,37 @@
 // Implicit-GEMM 3x3 / 1x1 convolution on tcgen05 tensor cores (sm_100a).
 //
-//   out[b,h,w,n] = scale * ( acc_scale * sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c] + bias[n]
-//                            + film[b,n] + residual[b,h,w,n] )
+//   out[b,h,w,n] = scale * ( acc_scale * ( sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c]
+//                                          + sum_c A2[b,h,w,c] * W2[n,c] )
+//                            + bias[n] + film[b,n] + residual[b,h,w,n] )
+//   stats[b,n] += (sum, sum of squares) of out over the pixels of the tile        (optional)
 //
 // Replaces the cuDNN convolutions behind ddpm_conv3x3 / ddpm_conv1x1 / NIN of the reference
-// (models/ncsnpp_utils/layers.py:112-156, 678-689) together with the Dense_0 bias add and the
-// (x + h)/sqrt(2) residual of ResnetBlockBigGANpp.forward (layerspp.py:311-323).
+// (models/ncsnpp_utils/layers.py:112-156, 678-689) together with the Dense_0 bias add, the 1x1
+// shortcut Conv_2 and the (x + h)/sqrt(2) residual of ResnetBlockBigGANpp.forward
+// (layerspp.py:311-323), and produces the statistics the NEXT GroupNorm needs, so that tensor is
+// never re-read just to be reduced.
 //
 // Design (B200-first):
-//   * activations are channels-last, so an output tile of 128 pixels x 64 input channels of one
-//     filter tap is ONE 4-D TMA box [64 ch, tw, th, tb] at coordinates shifted by (dx, dy);
-//     out-of-image taps are zero-filled by TMA — no im2col, no padding copies;
+//   * activations are channels-last, so the A tile of one filter tap (128 pixels x 64 channels)
+//     is ONE 4-D TMA box [64 ch, tw, th, tb] at coordinates shifted by (dx, dy); out-of-image
+//     taps are zero-filled by TMA — no im2col, no padding copies;
 //   * operands are (hi, lo) fp16 planes (weights pre-scaled by a power of two, undone by
-//     acc_scale); three tcgen05.mma passes hi*hi + lo*hi + hi*lo accumulate in fp32 in TMEM,
-//     which reproduces the fp32 convolution to ~1e-6 (passes = 1 gives TF32-grade 11-bit
-//     operands, what cuDNN runs for the reference by default on a GPU);
+//     acc_scale).  Per K=16 step two tcgen05.mma: A_hi x [W_hi ; W_lo] (the two weight planes
+//     stacked along N, N = 2 NT, into TMEM columns [0, 2NT)) and A_lo x W_hi (N = NT, columns
+//     [0, NT)); the epilogue adds the halves.  Same MAC count as three passes with 17 % less
+//     shared-memory operand traffic, and the small hi*lo terms accumulate apart from the large
+//     ones.  passes = 1 issues A_hi x W_hi only (11-bit operands: TF32-grade, what cuDNN runs
+//     for the reference by default on a GPU);
+//   * the 1x1 shortcut convolution is extra K-blocks from a second operand (A2, W2) accumulated
+//     into the same TMEM tile: its output is never written to or re-read from HBM;
 //   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer,
-//     warp 2 TMEM allocator, warps 4-7 epilogue; smem ring of NSTAGES K-blocks, TMEM
-//     accumulator double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   * epilogue: tcgen05.ld -> per-warp smem transpose -> bias/FiLM/residual/scale fused ->
-//     128-byte coalesced fp32 stores.
+//     warp 2 TMEM allocator, warps 4-11 epilogue (two warps per TMEM lane quarter, splitting
+//     the columns); smem ring of K-blocks with mbarrier full/empty pairs; the TMEM accumulator
+//     is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue: residual prefetched into registers, tcgen05.ld -> XOR-swizzled per-warp smem
+//     transpose (conflict-free both ways) -> bias/FiLM/residual/scale fused -> 128-byte
+//     coalesced fp32 stores; per-channel (sum, sum^2) reduced in registers + 2 shuffles and
+//     accumulated with fp64 atomics.
 #include <mutex>
 
 #include "common.cuh"
@@ -32,6 +44,7 @@ struct ConvParams {
     int tw_log2, th_log2;  // pixel tile: tw x th x tb = 128
     int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
     int kblocks;           // Cin / 64
+    int kblocks2;          // Cin2 / 64 of the fused 1x1 shortcut (0: none)
     int passes;            // 1 or 3
     const float* bias;
     const float* film;
@@ -39,21 +52,29 @@ struct ConvParams {
     const float* residual;
     float scale, acc_scale;
     float* out;
+    double* stats;         // [B, cout_store, 2] or null
 };
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
 
 template <int NT>
 struct ConvCfg {
     static constexpr int kStageBytes = 2 * 16384 + 2 * NT * 128;
-    static constexpr int kStages = NT >= 128 ? 3 : (NT >= 64 ? 4 : 5);
-    static constexpr int kStagingBytes = NT >= 32 ? 4 * 32 * 36 * 4 : 0;
-    static constexpr int kTmemCols = 2 * NT < 32 ? 32 : 2 * NT;
+    static constexpr int kStagingBytes = NT >= 64 ? kEpiWarps * 32 * 32 * 4 : 0;
+    static constexpr int kAvail = 232448 - 1024 - 256 - kStagingBytes;
+    static constexpr int kStagesMax = kAvail / kStageBytes;
+    static constexpr int kStages = kStagesMax > 6 ? 6 : kStagesMax;
+    static constexpr int kTmemCols = 4 * NT < 32 ? 32 : 4 * NT;   // 2 stages x (hi*hi+lo*hi | hi*lo)
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
 template <int NT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+               const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
+               const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                const ConvParams p) {
     using Cfg = ConvCfg<NT>;
     constexpr int NS = Cfg::kStages;
@@ -70,14 +91,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool three = p.passes == 3;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi);
         tma_prefetch_desc(&tm_w_hi);
-        if (p.passes == 3) {
-            tma_prefetch_desc(&tm_a_lo);
-            tma_prefetch_desc(&tm_w_lo);
-        }
+        if (three) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_w_lo); }
+        if (p.kblocks2 > 0) { tma_prefetch_desc(&tm_a2_hi); tma_prefetch_desc(&tm_w2_hi); }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NS; ++i) {
@@ -86,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], NT >= 64 ? kEpiWarps : 4);   // narrow tiles: only 4 warps drain TMEM
         }
         fence_mbar_init();
     }
@@ -97,8 +117,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const uint32_t tmem_base = *tmem_ptr;
 
     const int tb_log2 = 7 - p.tw_log2 - p.th_log2;
-    const int kiters = p.taps * p.kblocks;
-    const uint32_t stage_tx = (p.passes == 3 ? 2u : 1u) * (16384u + NT * 128u);
+    const int kiters = p.taps * p.kblocks + p.kblocks2;
+    const uint32_t stage_tx = (three ? 2u : 1u) * (16384u + NT * 128u);
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -111,27 +131,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int ht = r % p.tiles_h; r /= p.tiles_h;
             const int w0 = wt << p.tw_log2, h0 = ht << p.th_log2, b0 = r << tb_log2;
             const int n0 = nt * NT;
-            for (int tap = 0; tap < p.taps; ++tap) {
-                const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
-                const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
-                    uint8_t* s = stage_base + stage * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(&full[stage], stage_tx);
-                    tma_load_4d(s, &tm_a_hi, &full[stage], kb * 64, w0 + dx, h0 + dy, b0);
-                    tma_load_2d(s + 32768, &tm_w_hi, &full[stage], kb * 64, tap * p.Cout_pad + n0);
-                    if (p.passes == 3) {
-                        tma_load_4d(s + 16384, &tm_a_lo, &full[stage], kb * 64, w0 + dx, h0 + dy, b0);
-                        tma_load_2d(s + 32768 + NT * 128, &tm_w_lo, &full[stage], kb * 64,
-                                    tap * p.Cout_pad + n0);
-                    }
-                    if (++stage == NS) { stage = 0; phase ^= 1u; }
+            for (int ki = 0; ki < kiters; ++ki) {
+                const bool second = ki >= p.taps * p.kblocks;
+                int tap = 0, kb, dy = 0, dx = 0;
+                if (second) {
+                    kb = ki - p.taps * p.kblocks;
+                } else {
+                    tap = ki / p.kblocks;
+                    kb = ki - tap * p.kblocks;
+                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
                 }
+                mbar_wait(&empty[stage], phase ^ 1u);
+                uint8_t* s = stage_base + stage * Cfg::kStageBytes;
+                mbar_arrive_expect_tx(&full[stage], stage_tx);
+                const int wrow = second ? n0 : tap * p.Cout_pad + n0;
+                tma_load_4d(s, second ? &tm_a2_hi : &tm_a_hi, &full[stage], kb * 64, w0 + dx, h0 + dy, b0);
+                tma_load_2d(s + 32768, second ? &tm_w2_hi : &tm_w_hi, &full[stage], kb * 64, wrow);
+                if (three) {
+                    tma_load_4d(s + 16384, second ? &tm_a2_lo : &tm_a_lo, &full[stage], kb * 64, w0 + dx,
+                                h0 + dy, b0);
+                    tma_load_2d(s + 32768 + NT * 128, second ? &tm_w2_lo : &tm_w_lo, &full[stage], kb * 64, wrow);
+                }
+                if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_f16(128, NT);
+        constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
+        constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -139,7 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int as = it & 1;
             mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * NT;
+            const uint32_t d_tmem = tmem_base + as * 2 * NT;
             for (int ki = 0; ki < kiters; ++ki) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -147,13 +174,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t a_hi = umma_desc_sw128(s + k * 32);
-                    const uint64_t b_hi = umma_desc_sw128(s + 32768 + k * 32);
-                    umma_f16(d_tmem, a_hi, b_hi, idesc, (ki | k) != 0);
-                    if (p.passes == 3) {
+                    const uint64_t b_hi = umma_desc_sw128(s + 32768 + k * 32);   // W_hi rows, then W_lo rows
+                    if (three) {
+                        umma_f16(d_tmem, a_hi, b_hi, idesc_2n, (ki | k) != 0);
                         const uint64_t a_lo = umma_desc_sw128(s + 16384 + k * 32);
-                        const uint64_t b_lo = umma_desc_sw128(s + 32768 + NT * 128 + k * 32);
-                        umma_f16(d_tmem, a_lo, b_hi, idesc, 1);
-                        umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                        umma_f16(d_tmem, a_lo, b_hi, idesc_n, 1);
+                    } else {
+                        umma_f16(d_tmem, a_hi, b_hi, idesc_n, (ki | k) != 0);
                     }
                 }
                 umma_commit(&empty[stage]);   // frees the smem slot once these MMAs retire
@@ -163,7 +190,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
-        const int wq = warp - 4;              // TMEM lane quarter == warp_id % 4
+        const int ew = warp - 4;
+        const int wq = ew & 3;                // TMEM lane quarter == warp_id % 4
         const int tw_mask = (1 << p.tw_log2) - 1, th_mask = (1 << p.th_log2) - 1;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -174,83 +202,149 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int ht = r % p.tiles_h; r /= p.tiles_h;
             const int w0 = wt << p.tw_log2, h0 = ht << p.th_log2, b0 = r << tb_log2;
             const int n0 = nt * NT;
-            mbar_wait(&tfull[as], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * NT;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 2 * NT;
 
-            if constexpr (NT >= 32) {
-                float* stg = staging + wq * (32 * 36);
+            if constexpr (NT >= 64) {
+                constexpr int kChunks = NT / 64;          // 32-column chunks per warp
+                const int chalf = ew >> 2;                // which half of the tile's columns
+                float* stg = staging + ew * (32 * 32);
+                const int q = lane & 7, rg = lane >> 3;
+                // pixel of each of this thread's 8 output rows (row = i*4 + rg of this warp's 32)
+                size_t pix_off[8];
+                int bsel[8];
+                uint32_t valid = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = wq * 32 + i * 4 + rg;
+                    const int w = w0 + (m & tw_mask);
+                    const int h = h0 + ((m >> p.tw_log2) & th_mask);
+                    const int b = b0 + (m >> (p.tw_log2 + p.th_log2));
+                    const bool ok = b < p.B && h < p.H && w < p.W;
+                    valid |= (ok ? 1u : 0u) << i;
+                    bsel[i] = ok ? b : 0;
+                    pix_off[i] = ok ? ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.cout_store : 0;
+                }
+                bool waited = false;
 #pragma unroll 1
-                for (int c = 0; c < NT / 32; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
+                    const int col0 = chalf * (NT / 2) + c * 32;
+                    const int n = n0 + col0 + q * 4;
+                    const bool n_ok = n < p.cout_store;
+                    // prefetch the residual while the accumulator is still being produced / loaded
+                    float4 res[8];
+                    if (p.residual != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            res[i] = (n_ok && ((valid >> i) & 1u))
+                                         ? __ldg(reinterpret_cast<const float4*>(p.residual + pix_off[i] + n))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (!waited) {
+                        mbar_wait(&tfull[as], (it >> 1) & 1);
+                        tc_fence_after();
+                        waited = true;
+                    }
                     uint32_t v[32];
-                    tmem_ld_32x32(t_addr + c * 32, v);
-                    tmem_ld_wait();
-                    if (c == NT / 32 - 1) {   // TMEM fully drained: hand the buffer back early
+                    tmem_ld_32x32(t_addr + col0, v);
+                    if (three) {
+                        uint32_t u[32];
+                        tmem_ld_32x32(t_addr + NT + col0, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    if (c == kChunks - 1) {   // TMEM fully drained by this warp: hand the buffer back early
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[as]);
                     }
-                    float4* dst = reinterpret_cast<float4*>(stg + lane * 36);
+                    // transpose through smem: row = lane, 16-byte chunk j stored at j ^ (lane & 7)
+                    float4* dst = reinterpret_cast<float4*>(stg + lane * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        dst[j ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     __syncwarp();
-                    const int q = lane & 7;
-                    const int n = n0 + c * 32 + q * 4;
                     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const bool n_ok = n < p.cout_store;
-                    if (p.bias != nullptr && n_ok) bz = *reinterpret_cast<const float4*>(p.bias + n);
+                    if (p.bias != nullptr && n_ok) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + (lane >> 3);
-                        const int m = wq * 32 + row;
-                        const int w = w0 + (m & tw_mask);
-                        const int h = h0 + ((m >> p.tw_log2) & th_mask);
-                        const int b = b0 + (m >> (p.tw_log2 + p.th_log2));
-                        if (n_ok && b < p.B && h < p.H && w < p.W) {
-                            float4 a = *reinterpret_cast<const float4*>(stg + row * 36 + q * 4);
+                        const int row = i * 4 + rg;
+                        if (n_ok && ((valid >> i) & 1u)) {
+                            float4 a = *reinterpret_cast<const float4*>(stg + row * 32 + ((q ^ (row & 7)) << 2));
                             a.x = fmaf(a.x, p.acc_scale, bz.x); a.y = fmaf(a.y, p.acc_scale, bz.y);
                             a.z = fmaf(a.z, p.acc_scale, bz.z); a.w = fmaf(a.w, p.acc_scale, bz.w);
                             if (p.film != nullptr) {
-                                const float4 f = *reinterpret_cast<const float4*>(
-                                    p.film + static_cast<size_t>(b) * p.film_stride + n);
+                                const float4 f = __ldg(reinterpret_cast<const float4*>(
+                                    p.film + static_cast<size_t>(bsel[i]) * p.film_stride + n));
                                 a.x += f.x; a.y += f.y; a.z += f.z; a.w += f.w;
                             }
-                            const size_t off =
-                                ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.cout_store + n;
                             if (p.residual != nullptr) {
-                                const float4 rr = *reinterpret_cast<const float4*>(p.residual + off);
-                                a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+                                a.x += res[i].x; a.y += res[i].y; a.z += res[i].z; a.w += res[i].w;
                             }
                             a.x *= p.scale; a.y *= p.scale; a.z *= p.scale; a.w *= p.scale;
-                            *reinterpret_cast<float4*>(p.out + off) = a;
+                            *reinterpret_cast<float4*>(p.out + pix_off[i] + n) = a;
+                            s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+                            s2.x = fmaf(a.x, a.x, s2.x); s2.y = fmaf(a.y, a.y, s2.y);
+                            s2.z = fmaf(a.z, a.z, s2.z); s2.w = fmaf(a.w, a.w, s2.w);
+                        }
+                    }
+                    if (p.stats != nullptr) {
+                        // all 32 rows of this warp belong to one batch entry (host guarantees H*W >= 128)
+#pragma unroll
+                        for (int o = 8; o <= 16; o <<= 1) {
+                            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+                            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+                            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+                        }
+                        if (rg == 0 && n_ok && b0 < p.B) {
+                            double* st = p.stats + (static_cast<size_t>(b0) * p.cout_store + n) * 2;
+                            atomicAdd(st + 0, (double)s1.x); atomicAdd(st + 1, (double)s2.x);
+                            atomicAdd(st + 2, (double)s1.y); atomicAdd(st + 3, (double)s2.y);
+                            atomicAdd(st + 4, (double)s1.z); atomicAdd(st + 5, (double)s2.z);
+                            atomicAdd(st + 6, (double)s1.w); atomicAdd(st + 7, (double)s2.w);
                         }
                     }
                     __syncwarp();
                 }
             } else {
-                // narrow output (pyramid convs, Cout = 6 padded to 16): thread == pixel
-                uint32_t v[16];
-                tmem_ld_32x16(t_addr, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[as]);
-                const int m = wq * 32 + lane;
-                const int w = w0 + (m & tw_mask);
-                const int h = h0 + ((m >> p.tw_log2) & th_mask);
-                const int b = b0 + (m >> (p.tw_log2 + p.th_log2));
-                if (b < p.B && h < p.H && w < p.W) {
-                    const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.cout_store;
+                // narrow output (pyramid convs, Cout = 6 padded to 16): thread == pixel; warps 8-11 idle
+                if (ew < 4) {
+                    mbar_wait(&tfull[as], (it >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_addr, v);
+                    if (three) {
+                        uint32_t u[16];
+                        tmem_ld_32x16(t_addr + NT, u);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) {
-                        if (n < p.cout_store) {
-                            float a = __uint_as_float(v[n]) * p.acc_scale;
-                            if (p.bias != nullptr) a += p.bias[n];
-                            if (p.film != nullptr) a += p.film[static_cast<size_t>(b) * p.film_stride + n];
-                            if (p.residual != nullptr) a += p.residual[off + n];
-                            p.out[off + n] = a * p.scale;
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    const int m = wq * 32 + lane;
+                    const int w = w0 + (m & tw_mask);
+                    const int h = h0 + ((m >> p.tw_log2) & th_mask);
+                    const int b = b0 + (m >> (p.tw_log2 + p.th_log2));
+                    if (b < p.B && h < p.H && w < p.W) {
+                        const size_t off = ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.cout_store;
+#pragma unroll
+                        for (int n = 0; n < 16; ++n) {
+                            if (n < p.cout_store) {
+                                float a = __uint_as_float(v[n]) * p.acc_scale;
+                                if (p.bias != nullptr) a += p.bias[n];
+                                if (p.film != nullptr) a += p.film[static_cast<size_t>(b) * p.film_stride + n];
+                                if (p.residual != nullptr) a += p.residual[off + n];
+                                p.out[off + n] = a * p.scale;
+                            }
                         }
                     }
                 }
@@ -311,9 +405,12 @@ static int num_sms() {
     return n;
 }
 
+struct ConvMaps {
+    CUtensorMap a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, w2_hi, w2_lo;
+};
+
 template <int NT>
-static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const ConvParams& p, cudaStream_t stream) {
+static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -325,7 +422,8 @@ static int launch_conv(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
         return DSEP_ERR_CUDA;
     }
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_kernel<NT><<<grid, 256, ConvCfg<NT>::kSmemBytes, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+    conv_tc_kernel<NT><<<grid, kThreads, ConvCfg<NT>::kSmemBytes, stream>>>(
+        m.a_hi, m.a_lo, m.w_hi, m.w_lo, m.a2_hi, m.a2_lo, m.w2_hi, m.w2_lo, p);
     return check_launch("conv_tc_kernel");
 }
 
@@ -339,9 +437,10 @@ static int ilog2(int v) {
 
 extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
                               const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
-                              const float* bias, const float* film, int film_stride,
+                              const void* a2_hi, const void* a2_lo, int Cin2, const void* w2_hi,
+                              const void* w2_lo, const float* bias, const float* film, int film_stride,
                               const float* residual, float scale, float acc_scale, float* out,
-                              int cout_store, int passes, dsep_stream_t stream) {
+                              int cout_store, double* stats, int passes, dsep_stream_t stream) {
     using namespace dsep;
     DSEP_REQUIRE(a_hi && w_hi && out, "conv2d_tc: null operand");
     DSEP_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3 (got %d)", passes);
@@ -353,6 +452,9 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
                  "conv2d_tc: Cout_pad must be 16 or a multiple of 64 (got %d)", Cout_pad);
     DSEP_REQUIRE(cout_store > 0 && cout_store <= Cout_pad, "conv2d_tc: bad cout_store %d", cout_store);
     DSEP_REQUIRE(Cout_pad == 16 || cout_store % 4 == 0, "conv2d_tc: cout_store must be a multiple of 4");
+    DSEP_REQUIRE(Cin2 >= 0 && Cin2 % 64 == 0, "conv2d_tc: Cin2 must be a multiple of 64 (got %d)", Cin2);
+    DSEP_REQUIRE(Cin2 == 0 || (a2_hi && w2_hi && (passes == 1 || (a2_lo && w2_lo))),
+                 "conv2d_tc: fused 1x1 operand (Cin2=%d) needs its activation and weight planes", Cin2);
     const int NT = Cout_pad == 16 ? 16 : (Cout_pad % 128 == 0 ? 128 : 64);
 
     ConvParams p{};
@@ -361,36 +463,61 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     int tw = 1 << ilog2(W); if (tw > 16) tw = 16;
     int th = 1 << ilog2(H); if (th > 128 / tw) th = 128 / tw;
     const int tb = 128 / (tw * th);
+    DSEP_REQUIRE(stats == nullptr || (Cout_pad != 16 && tb == 1),
+                 "conv2d_tc: fused statistics need Cout >= 64 and 128-pixel tiles inside one batch entry "
+                 "(got %dx%d, tile %dx%dx%d)", H, W, th, tw, tb);
     p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
     p.tiles_w = ceil_div(W, tw); p.tiles_h = ceil_div(H, th); p.tiles_b = ceil_div(B, tb);
     p.tiles_n = Cout_pad / NT;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
     p.kblocks = Cin / 64;
+    p.kblocks2 = Cin2 / 64;
     p.passes = passes;
     p.bias = bias; p.film = film; p.film_stride = film_stride; p.residual = residual;
-    p.scale = scale; p.acc_scale = acc_scale; p.out = out;
+    p.scale = scale; p.acc_scale = acc_scale; p.out = out; p.stats = stats;
 
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    const cuuint32_t abox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
-    const cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)p.taps * Cout_pad};
-    const cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
-    const cuuint32_t wbox[2] = {64, (cuuint32_t)NT};
+    ConvMaps m;
     int rc;
-    if ((rc = make_map(&ma_hi, a_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
-    if ((rc = make_map(&mw_hi, w_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
-    if (passes == 3) {
-        if ((rc = make_map(&ma_lo, a_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
-        if ((rc = make_map(&mw_lo, w_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+    {
+        const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        const cuuint32_t abox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+        const cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)p.taps * Cout_pad};
+        const cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
+        const cuuint32_t wbox[2] = {64, (cuuint32_t)NT};
+        if ((rc = make_map(&m.a_hi, a_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
+        if ((rc = make_map(&m.w_hi, w_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+        if (passes == 3) {
+            if ((rc = make_map(&m.a_lo, a_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
+            if ((rc = make_map(&m.w_lo, w_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+        } else {
+            m.a_lo = m.a_hi;
+            m.w_lo = m.w_hi;
+        }
+    }
+    if (Cin2 > 0) {
+        const cuuint64_t adims[4] = {(cuuint64_t)Cin2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t astr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)W * Cin2 * 2, (cuuint64_t)H * W * Cin2 * 2};
+        const cuuint32_t abox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+        const cuuint64_t wdims[2] = {(cuuint64_t)Cin2, (cuuint64_t)Cout_pad};
+        const cuuint64_t wstr[1] = {(cuuint64_t)Cin2 * 2};
+        const cuuint32_t wbox[2] = {64, (cuuint32_t)NT};
+        if ((rc = make_map(&m.a2_hi, a2_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
+        if ((rc = make_map(&m.w2_hi, w2_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+        if (passes == 3) {
+            if ((rc = make_map(&m.a2_lo, a2_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
+            if ((rc = make_map(&m.w2_lo, w2_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+        } else {
+            m.a2_lo = m.a2_hi;
+            m.w2_lo = m.w2_hi;
+        }
     } else {
-        ma_lo = ma_hi;
-        mw_lo = mw_hi;
+        m.a2_hi = m.a_hi; m.a2_lo = m.a_lo; m.w2_hi = m.w_hi; m.w2_lo = m.w_lo;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (NT) {
-        case 16: return launch_conv<16>(ma_hi, ma_lo, mw_hi, mw_lo, p, s);
-        case 64: return launch_conv<64>(ma_hi, ma_lo, mw_hi, mw_lo, p, s);
-        default: return launch_conv<128>(ma_hi, ma_lo, mw_hi, mw_lo, p, s);
+        case 16: return launch_conv<16>(m, p, s);
+        case 64: return launch_conv<64>(m, p, s);
+        default: return launch_conv<128>(m, p, s);
     }
 }

@@ -50,85 +50,114 @@ __global__ void split_kernel(const float* __restrict__ x, int64_t n4, float pres
     }
 }
 
-// ---------------------------------------------------------------------------- GN statistics
-// grid (chunks, B); thread t owns channel-quad (t % Q) of pixels (t / Q) + k*ppi of its chunk.
+// ---------------------------------------------------------------------------- channel statistics
+// stats[b, c, 0..1] += (sum, sum of squares) of x[b, :, c].  grid (chunks, B); thread t owns channel
+// quad (t % Q) of pixels (t / Q) + k*ppi of its chunk; fp64 accumulation end to end.
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int P,
-                int groups, int pix_per_block, double* __restrict__ stats) {
-    __shared__ double s_sum[64], s_sq[64];
-    const int Ct = C0 + C1, Q = Ct >> 2, cpg = Ct / groups;
+channel_stats_kernel(const float* __restrict__ x, int C, int P, int pix_per_block, double* __restrict__ stats) {
+    extern __shared__ double s_acc[];   // [C][2]
+    const int Q = C >> 2;
     const int b = blockIdx.y;
-    if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
     const int ppi = blockDim.x / Q;
     const int q = threadIdx.x % Q, j = threadIdx.x / Q;
     if (j < ppi) {
-        const int c = q * 4;
-        const float* src;
-        int cs, cl;
-        if (c < C0) { src = x0; cs = C0; cl = c; } else { src = x1; cs = C1; cl = c - C0; }
         const int p_begin = blockIdx.x * pix_per_block;
         const int p_end = min(P, p_begin + pix_per_block);
-        // the quad may straddle two groups when a group has only 2 channels (nf = 64)
-        double s01 = 0.0, ss01 = 0.0, s23 = 0.0, ss23 = 0.0;
+        double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+        const float* src = x + static_cast<size_t>(b) * P * C + q * 4;
         for (int p = p_begin + j; p < p_end; p += ppi) {
-            const float4 v = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * P + p) * cs + cl);
-            s01 += (double)v.x + (double)v.y;
-            s23 += (double)v.z + (double)v.w;
-            ss01 += (double)v.x * v.x + (double)v.y * v.y;
-            ss23 += (double)v.z * v.z + (double)v.w * v.w;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(p) * C));
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            ss[0] += (double)v.x * v.x; ss[1] += (double)v.y * v.y;
+            ss[2] += (double)v.z * v.z; ss[3] += (double)v.w * v.w;
         }
-        const int g0 = c / cpg, g1 = (c + 2) / cpg;
-        if (g0 == g1) {
-            atomicAdd(&s_sum[g0], s01 + s23);
-            atomicAdd(&s_sq[g0], ss01 + ss23);
-        } else {
-            atomicAdd(&s_sum[g0], s01); atomicAdd(&s_sq[g0], ss01);
-            atomicAdd(&s_sum[g1], s23); atomicAdd(&s_sq[g1], ss23);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            atomicAdd(&s_acc[(q * 4 + u) * 2 + 0], s[u]);
+            atomicAdd(&s_acc[(q * 4 + u) * 2 + 1], ss[u]);
         }
     }
     __syncthreads();
-    if (threadIdx.x < groups) {
-        atomicAdd(&stats[(static_cast<size_t>(b) * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-        atomicAdd(&stats[(static_cast<size_t>(b) * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
-    }
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+        atomicAdd(&stats[static_cast<size_t>(b) * 2 * C + i], s_acc[i]);
 }
 
-__device__ __forceinline__ void gn_finalize(const double* stats, int b, int groups, int g, double count,
-                                            float eps, float& mean, float& rstd) {
-    const double s = stats[(static_cast<size_t>(b) * groups + g) * 2 + 0];
-    const double ss = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
-    const double m = s / count;
-    double var = ss / count - m * m;
-    if (var < 0.0) var = 0.0;
-    mean = static_cast<float>(m);
-    rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+// Per-channel GroupNorm scale / shift of batch entry b from per-channel sums of a (possibly
+// concatenated) input: y = x * sc[c] + sh[c].  Block-wide; s_sc / s_sh have Ct entries.
+__device__ __forceinline__ void gn_tables(const double* __restrict__ st0, int C0, const double* __restrict__ st1,
+                                          int C1, int b, int groups, double count_per_channel,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          float eps, float* s_sc, float* s_sh, float* s_mean, float* s_rstd) {
+    const int Ct = C0 + C1, cpg = Ct / groups;
+    if (st0 == nullptr) {
+        for (int c = threadIdx.x; c < Ct; c += blockDim.x) { s_sc[c] = 1.0f; s_sh[c] = 0.0f; }
+        __syncthreads();
+        return;
+    }
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, ss = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const double* st = c < C0 ? st0 + (static_cast<size_t>(b) * C0 + c) * 2
+                                      : st1 + (static_cast<size_t>(b) * C1 + (c - C0)) * 2;
+            s += st[0];
+            ss += st[1];
+        }
+        const double n = count_per_channel * cpg;
+        const double m = s / n;
+        double var = ss / n - m * m;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(m);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = gamma[c] * s_rstd[g];
+        s_sc[c] = sc;
+        s_sh[c] = beta[c] - s_mean[g] * sc;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float4 affine_act(const float4 v, const float4 sc, const float4 sh, bool act) {
+    float4 y;
+    y.x = fmaf(v.x, sc.x, sh.x); y.y = fmaf(v.y, sc.y, sh.y);
+    y.z = fmaf(v.z, sc.z, sh.z); y.w = fmaf(v.w, sc.w, sh.w);
+    if (act) { y.x = silu_fast(y.x); y.y = silu_fast(y.y); y.z = silu_fast(y.z); y.w = silu_fast(y.w); }
+    return y;
 }
 
 // ------------------------------------------------------- GN + act + split (+ raw split)
-// grid (chunks, B); each thread converts one channel-quad of one pixel per iteration.
+// grid (chunks, B); each thread converts one channel-quad of one pixel per step, two steps in flight.
 __global__ void __launch_bounds__(256)
-gn_act_split_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int P,
-                    int groups, const double* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, float eps, int act, f16x4* __restrict__ a_hi,
-                    f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi, f16x4* __restrict__ r_lo,
-                    int pix_per_block) {
-    __shared__ float s_mean[64], s_rstd[64];
-    const int Ct = C0 + C1, Q = Ct >> 2, cpg = Ct / groups;
+gn_act_split_kernel(const float* __restrict__ x0, int C0, const double* __restrict__ st0,
+                    const float* __restrict__ x1, int C1, const double* __restrict__ st1, int P, int groups,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
+                    f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
+                    f16x4* __restrict__ r_lo, int pix_per_block) {
+    extern __shared__ float s_tab[];   // sc[Ct] | sh[Ct] | mean[64] | rstd[64]
+    const int Ct = C0 + C1, Q = Ct >> 2;
+    float* s_sc = s_tab;
+    float* s_sh = s_tab + Ct;
     const int b = blockIdx.y;
-    if (stats != nullptr && threadIdx.x < groups)
-        gn_finalize(stats, b, groups, threadIdx.x, (double)P * cpg, eps, s_mean[threadIdx.x],
-                    s_rstd[threadIdx.x]);
-    __syncthreads();
+    gn_tables(st0, C0, st1, C1, b, groups, (double)P, gamma, beta, eps, s_sc, s_sh, s_tab + 2 * Ct,
+              s_tab + 2 * Ct + 64);
     const int64_t e_begin = (int64_t)blockIdx.x * pix_per_block * Q;
     const int64_t e_end = min((int64_t)P * Q, e_begin + (int64_t)pix_per_block * Q);
-    for (int64_t e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
-        const int p = static_cast<int>(e / Q), q = static_cast<int>(e % Q);
+    const bool on = act != 0;
+    auto load = [&](int64_t e, int& q) -> float4 {
+        const int p = static_cast<int>(e / Q);
+        q = static_cast<int>(e - (int64_t)p * Q);
         const int c = q * 4;
-        const float4 v = c < C0
-            ? *reinterpret_cast<const float4*>(x0 + (static_cast<size_t>(b) * P + p) * C0 + c)
-            : *reinterpret_cast<const float4*>(x1 + (static_cast<size_t>(b) * P + p) * C1 + (c - C0));
-        const size_t o = (static_cast<size_t>(b) * P + p) * Q + q;
+        return c < C0 ? __ldg(reinterpret_cast<const float4*>(x0 + (static_cast<size_t>(b) * P + p) * C0 + c))
+                      : __ldg(reinterpret_cast<const float4*>(x1 + (static_cast<size_t>(b) * P + p) * C1 + (c - C0)));
+    };
+    auto emit = [&](int64_t e, int q, const float4 v) {
+        const size_t o = static_cast<size_t>(b) * P * Q + e;
         f16x4 h, l;
         if (r_hi != nullptr) {
             split4(v, h, l);
@@ -136,101 +165,150 @@ gn_act_split_kernel(const float* __restrict__ x0, int C0, const float* __restric
             r_lo[o] = l;
         }
         if (a_hi != nullptr) {
-            float4 y = v;
-            if (stats != nullptr) {
-                const int g0 = c / cpg, g1 = (c + 2) / cpg;
-                const float m0 = s_mean[g0], rs0 = s_rstd[g0], m1 = s_mean[g1], rs1 = s_rstd[g1];
-                const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
-                const float4 be = *reinterpret_cast<const float4*>(beta + c);
-                y.x = (v.x - m0) * rs0 * ga.x + be.x;
-                y.y = (v.y - m0) * rs0 * ga.y + be.y;
-                y.z = (v.z - m1) * rs1 * ga.z + be.z;
-                y.w = (v.w - m1) * rs1 * ga.w + be.w;
-            }
-            if (act == 1) { y.x = silu_f(y.x); y.y = silu_f(y.y); y.z = silu_f(y.z); y.w = silu_f(y.w); }
-            split4(y, h, l);
+            const float4 sc = *reinterpret_cast<const float4*>(s_sc + q * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_sh + q * 4);
+            split4(affine_act(v, sc, sh, on), h, l);
             a_hi[o] = h;
             a_lo[o] = l;
         }
+    };
+    int64_t e = e_begin + threadIdx.x;
+    for (; e + blockDim.x < e_end; e += 2 * blockDim.x) {
+        int q0, q1;
+        const float4 v0 = load(e, q0);
+        const float4 v1 = load(e + blockDim.x, q1);
+        emit(e, q0, v0);
+        emit(e + blockDim.x, q1, v1);
+    }
+    if (e < e_end) {
+        int q0;
+        const float4 v0 = load(e, q0);
+        emit(e, q0, v0);
     }
 }
 
 // --------------------------------------------------------------------------- FIR resample
 // taps [1,3,3,1]; down: y[i] = (x[2i-1] + 3x[2i] + 3x[2i+1] + x[2i+2]) / 8 per axis;
 // up (gain 2 per axis): y[2i] = (x[i-1] + 3x[i]) / 4, y[2i+1] = (3x[i] + x[i+1]) / 4; zeros outside.
-template <int MODE>   // 1 up, 2 down
+//
+// Tiled: a block stages the input patch of one (batch entry, spatial tile, 32-channel chunk) in shared
+// memory ONCE — with GroupNorm+SiLU already applied, so the transcendental is evaluated once per
+// input element instead of once per tap — and then forms every output of the tile from it.
+//   MODE 2 (down): 4 x 8 output pixels  <- 10 x 18 input pixels
+//   MODE 1 (up):  16 x 16 output pixels <- 10 x 10 input pixels (8 x 8 + halo)
+template <int MODE>
+struct FirTile {
+    static constexpr int OH = MODE == 1 ? 16 : 4, OW = MODE == 1 ? 16 : 8;
+    static constexpr int IH = MODE == 1 ? 10 : 10, IW = MODE == 1 ? 10 : 18;
+    static constexpr int kSmemBytes = 2 * IH * IW * 32 * 4;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
-fir_quad_kernel(const float* __restrict__ x, int H, int W, int C, int groups,
-                const double* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, f16x4* __restrict__ a_hi,
-                f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi, f16x4* __restrict__ r_lo,
-                float4* __restrict__ y, int pix_per_block) {
-    __shared__ float s_mean[64], s_rstd[64];
-    const int Q = C >> 2;
-    const int b = blockIdx.y;
-    const bool xf = stats != nullptr && a_hi != nullptr;
-    const int cpg = xf ? C / groups : 1;
-    if (xf && threadIdx.x < groups)
-        gn_finalize(stats, b, groups, threadIdx.x, (double)H * W * cpg, eps, s_mean[threadIdx.x],
-                    s_rstd[threadIdx.x]);
-    __syncthreads();
+fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, const double* __restrict__ st,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
+                f16x4* __restrict__ r_lo, float4* __restrict__ y, int tiles_w, int tiles_h) {
+    using FT = FirTile<MODE>;
+    extern __shared__ __align__(16) float s_fir[];
+    float4* s_act = reinterpret_cast<float4*>(s_fir);                  // [IH*IW][8 quads]
+    float4* s_raw = s_act + FT::IH * FT::IW * 8;
+    __shared__ float s_sc[32], s_sh[32];
     const int Ho = MODE == 1 ? H * 2 : H / 2, Wo = MODE == 1 ? W * 2 : W / 2;
-    const int64_t e_begin = (int64_t)blockIdx.x * pix_per_block * Q;
-    const int64_t e_end = min((int64_t)Ho * Wo * Q, e_begin + (int64_t)pix_per_block * Q);
-    const bool want_raw = (r_hi != nullptr) || (y != nullptr);
-    for (int64_t e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
-        const int q = static_cast<int>(e % Q);
-        const int po = static_cast<int>(e / Q);
-        const int oi = po / Wo, oj = po % Wo;
-        const int c = q * 4;
-        float m0 = 0.f, rs0 = 1.f, m1 = 0.f, rs1 = 1.f;
-        float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int chunk = blockIdx.y, b = blockIdx.z;
+    const int tw_i = blockIdx.x % tiles_w, th_i = blockIdx.x / tiles_w;
+    const int oh0 = th_i * FT::OH, ow0 = tw_i * FT::OW;
+    const int ih0 = MODE == 1 ? oh0 / 2 - 1 : oh0 * 2 - 1;
+    const int iw0 = MODE == 1 ? ow0 / 2 - 1 : ow0 * 2 - 1;
+    const int c0 = chunk * 32;
+    const bool xf = st != nullptr && a_hi != nullptr;
+    const bool want_raw = r_hi != nullptr || y != nullptr;
+    if (threadIdx.x < 32) {
+        float sc = 1.0f, sh = 0.0f;
         if (xf) {
-            const int g0 = c / cpg, g1 = (c + 2) / cpg;
-            m0 = s_mean[g0]; rs0 = s_rstd[g0]; m1 = s_mean[g1]; rs1 = s_rstd[g1];
-            ga = *reinterpret_cast<const float4*>(gamma + c);
-            be = *reinterpret_cast<const float4*>(beta + c);
+            const int cpg = C / groups, c = c0 + threadIdx.x, g = c / cpg;
+            double s = 0.0, ss = 0.0;
+            for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+                s += st[(static_cast<size_t>(b) * C + cc) * 2 + 0];
+                ss += st[(static_cast<size_t>(b) * C + cc) * 2 + 1];
+            }
+            const double n = (double)H * W * cpg, m = s / n;
+            double var = ss / n - m * m;
+            if (var < 0.0) var = 0.0;
+            sc = gamma[c] * static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            sh = beta[c] - static_cast<float>(m) * sc;
         }
-        float4 acc_r = make_float4(0.f, 0.f, 0.f, 0.f), acc_a = acc_r;
-        constexpr int NTAP = MODE == 1 ? 2 : 4;
-        int i0, j0;
-        float wi[NTAP], wj[NTAP];
+        s_sc[threadIdx.x] = sc;
+        s_sh[threadIdx.x] = sh;
+    }
+    __syncthreads();
+    // stage the patch: out-of-image pixels are zero AFTER the activation (the FIR pads its input)
+    for (int i = threadIdx.x; i < FT::IH * FT::IW * 8; i += blockDim.x) {
+        const int q = i & 7, pix = i >> 3;
+        const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
+        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), av = raw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            raw = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + ih) * W + iw) * C + c0 + q * 4));
+            if (a_hi != nullptr)
+                av = xf ? affine_act(raw, *reinterpret_cast<const float4*>(s_sc + q * 4),
+                                     *reinterpret_cast<const float4*>(s_sh + q * 4), true)
+                        : raw;
+        }
+        s_act[i] = av;
+        s_raw[i] = raw;
+    }
+    __syncthreads();
+    const int Q = C >> 2;
+    for (int i = threadIdx.x; i < FT::OH * FT::OW * 8; i += blockDim.x) {
+        const int q = i & 7, opix = i >> 3;
+        const int oy = opix / FT::OW, ox = opix % FT::OW;
+        const int oh = oh0 + oy, ow = ow0 + ox;
+        if (oh >= Ho || ow >= Wo) continue;
+        float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_r = acc_a;
         if (MODE == 1) {
-            // even output 2i: taps (i-1: 1/4, i: 3/4); odd 2i+1: (i: 3/4, i+1: 1/4)
-            const int ii = oi >> 1, jj = oj >> 1;
-            if (oi & 1) { i0 = ii; wi[0] = 0.75f; wi[1] = 0.25f; } else { i0 = ii - 1; wi[0] = 0.25f; wi[1] = 0.75f; }
-            if (oj & 1) { j0 = jj; wj[0] = 0.75f; wj[1] = 0.25f; } else { j0 = jj - 1; wj[0] = 0.25f; wj[1] = 0.75f; }
-        } else {
-            i0 = 2 * oi - 1; j0 = 2 * oj - 1;
-            wi[0] = 0.125f; wi[1] = 0.375f; wi[2] = 0.375f; wi[3] = 0.125f;
-            wj[0] = 0.125f; wj[1] = 0.375f; wj[2] = 0.375f; wj[3] = 0.125f;
-        }
+            // patch row of input pixel (oh/2) is oy/2 + 1; even outputs use (i-1, i), odd (i, i+1)
+            const int py = (oy >> 1) + ((oy & 1) ? 1 : 0), px = (ox >> 1) + ((ox & 1) ? 1 : 0);
+            const float wy0 = (oy & 1) ? 0.75f : 0.25f, wx0 = (ox & 1) ? 0.75f : 0.25f;
 #pragma unroll
-        for (int a = 0; a < NTAP; ++a) {
-            const int i = i0 + a;
-            if (i < 0 || i >= H) continue;
+            for (int a = 0; a < 2; ++a) {
 #pragma unroll
-            for (int d = 0; d < NTAP; ++d) {
-                const int j = j0 + d;
-                if (j < 0 || j >= W) continue;
-                const float wgt = wi[a] * wj[d];
-                const float4 v = *reinterpret_cast<const float4*>(
-                    x + ((static_cast<size_t>(b) * H + i) * W + j) * C + c);
-                if (want_raw) {
-                    acc_r.x += wgt * v.x; acc_r.y += wgt * v.y; acc_r.z += wgt * v.z; acc_r.w += wgt * v.w;
-                }
-                if (a_hi != nullptr) {
-                    float4 t = v;
-                    if (xf) {
-                        t.x = (v.x - m0) * rs0 * ga.x + be.x; t.y = (v.y - m0) * rs0 * ga.y + be.y;
-                        t.z = (v.z - m1) * rs1 * ga.z + be.z; t.w = (v.w - m1) * rs1 * ga.w + be.w;
-                        t.x = silu_f(t.x); t.y = silu_f(t.y); t.z = silu_f(t.z); t.w = silu_f(t.w);
+                for (int d = 0; d < 2; ++d) {
+                    const float wgt = (a == 0 ? wy0 : 1.0f - wy0) * (d == 0 ? wx0 : 1.0f - wx0);
+                    const int si = ((py + a) * FT::IW + (px + d)) * 8 + q;
+                    if (a_hi != nullptr) {
+                        const float4 t = s_act[si];
+                        acc_a.x = fmaf(wgt, t.x, acc_a.x); acc_a.y = fmaf(wgt, t.y, acc_a.y);
+                        acc_a.z = fmaf(wgt, t.z, acc_a.z); acc_a.w = fmaf(wgt, t.w, acc_a.w);
                     }
-                    acc_a.x += wgt * t.x; acc_a.y += wgt * t.y; acc_a.z += wgt * t.z; acc_a.w += wgt * t.w;
+                    if (want_raw) {
+                        const float4 t = s_raw[si];
+                        acc_r.x = fmaf(wgt, t.x, acc_r.x); acc_r.y = fmaf(wgt, t.y, acc_r.y);
+                        acc_r.z = fmaf(wgt, t.z, acc_r.z); acc_r.w = fmaf(wgt, t.w, acc_r.w);
+                    }
+                }
+            }
+        } else {
+            const float wt[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const float wgt = wt[a] * wt[d];
+                    const int si = ((2 * oy + a) * FT::IW + (2 * ox + d)) * 8 + q;
+                    if (a_hi != nullptr) {
+                        const float4 t = s_act[si];
+                        acc_a.x = fmaf(wgt, t.x, acc_a.x); acc_a.y = fmaf(wgt, t.y, acc_a.y);
+                        acc_a.z = fmaf(wgt, t.z, acc_a.z); acc_a.w = fmaf(wgt, t.w, acc_a.w);
+                    }
+                    if (want_raw) {
+                        const float4 t = s_raw[si];
+                        acc_r.x = fmaf(wgt, t.x, acc_r.x); acc_r.y = fmaf(wgt, t.y, acc_r.y);
+                        acc_r.z = fmaf(wgt, t.z, acc_r.z); acc_r.w = fmaf(wgt, t.w, acc_r.w);
+                    }
                 }
             }
         }
-        const size_t o = (static_cast<size_t>(b) * Ho * Wo + po) * Q + q;
+        const size_t o = ((static_cast<size_t>(b) * Ho + oh) * Wo + ow) * Q + chunk * 8 + q;
         f16x4 h, l;
         if (a_hi != nullptr) { split4(acc_a, h, l); a_hi[o] = h; a_lo[o] = l; }
         if (r_hi != nullptr) { split4(acc_r, h, l); r_hi[o] = h; r_lo[o] = l; }
@@ -358,63 +436,94 @@ extern "C" int dsep_split_f16(const float* x, int64_t n, float prescale, void* h
 static int check_gn_shape(const char* who, int C0, int C1, int groups) {
     const int Ct = C0 + C1;
     DSEP_REQUIRE(C0 > 0 && C1 >= 0 && C0 % 4 == 0 && C1 % 4 == 0, "%s: channel counts must be multiples of 4", who);
-    DSEP_REQUIRE(groups > 0 && groups <= 64 && Ct % groups == 0 &&
-                     (Ct / groups) % 2 == 0,
-                 "%s: unsupported groups=%d for %d channels", who, groups, Ct);
-    DSEP_REQUIRE(Ct / 4 <= 256, "%s: at most 1024 channels", who);
+    DSEP_REQUIRE(groups > 0 && groups <= 64 && Ct % groups == 0, "%s: unsupported groups=%d for %d channels", who,
+                 groups, Ct);
+    DSEP_REQUIRE(Ct <= 1024, "%s: at most 1024 channels", who);
     return DSEP_OK;
 }
 
-extern "C" int dsep_gn_stats(const float* x0, int C0, const float* x1, int C1, int B, int P, int groups,
-                             double* stats, dsep_stream_t stream) {
-    DSEP_REQUIRE(x0 && stats && (C1 == 0 || x1), "gn_stats: null pointer");
-    DSEP_REQUIRE(B > 0 && P > 0, "gn_stats: empty tensor");
-    int rc = check_gn_shape("gn_stats", C0, C1, groups);
-    if (rc) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, s);
-    const int ppb = pix_per_block_for(P, B);
-    dim3 grid(ceil_div(P, ppb), B);
-    gn_stats_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, P, groups, ppb, stats);
-    return check_launch("gn_stats_kernel");
+extern "C" int dsep_zero(void* ptr, int64_t bytes, dsep_stream_t stream) {
+    DSEP_REQUIRE(ptr && bytes >= 0, "zero: bad arguments");
+    if (bytes == 0) return DSEP_OK;
+    cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("zero: %s", cudaGetErrorString(e));
+        return DSEP_ERR_CUDA;
+    }
+    return DSEP_OK;
 }
 
-extern "C" int dsep_gn_act_split(const float* x0, int C0, const float* x1, int C1, int B, int P,
-                                 int groups, const double* stats, const float* gamma, const float* beta,
-                                 float eps, int act, void* a_hi, void* a_lo, void* r_hi, void* r_lo,
-                                 dsep_stream_t stream) {
-    DSEP_REQUIRE(x0 && (C1 == 0 || x1), "gn_act_split: null input");
-    DSEP_REQUIRE((a_hi && a_lo) || (r_hi && r_lo), "gn_act_split: no output requested");
-    DSEP_REQUIRE(stats == nullptr || (gamma && beta), "gn_act_split: stats without gamma/beta");
-    DSEP_REQUIRE(act == 0 || act == 1, "gn_act_split: act must be 0 or 1");
-    DSEP_REQUIRE(B > 0 && P > 0, "gn_act_split: empty tensor");
-    DSEP_REQUIRE(C0 > 0 && C1 >= 0 && C0 % 4 == 0 && C1 % 4 == 0,
-                 "gn_act_split: channel counts must be multiples of 4");
-    if (stats) {
-        int rc = check_gn_shape("gn_act_split", C0, C1, groups);
-        if (rc) return rc;
-    }
+extern "C" int dsep_channel_stats(const float* x, int C, int B, int P, double* stats, dsep_stream_t stream) {
+    DSEP_REQUIRE(x && stats, "channel_stats: null pointer");
+    DSEP_REQUIRE(B > 0 && P > 0 && B <= 65535, "channel_stats: empty tensor");
+    DSEP_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024, "channel_stats: C must be a multiple of 4, at most 1024");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * C, s);
     const int ppb = pix_per_block_for(P, B);
     dim3 grid(ceil_div(P, ppb), B);
-    gn_act_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        x0, C0, x1, C1, P, stats ? groups : 1, stats, gamma, beta, eps, act, (f16x4*)a_hi, (f16x4*)a_lo,
-        (f16x4*)r_hi, (f16x4*)r_lo, ppb);
+    channel_stats_kernel<<<grid, 256, sizeof(double) * 2 * C, s>>>(x, C, P, ppb, stats);
+    return check_launch("channel_stats_kernel");
+}
+
+extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x1, int C1,
+                                 const double* st1, int B, int P, int groups, const float* gamma,
+                                 const float* beta, float eps, int act, void* a_hi, void* a_lo, void* r_hi,
+                                 void* r_lo, dsep_stream_t stream) {
+    DSEP_REQUIRE(x0 && (C1 == 0 || x1), "gn_act_split: null input");
+    DSEP_REQUIRE((a_hi && a_lo) || (r_hi && r_lo), "gn_act_split: no output requested");
+    DSEP_REQUIRE(st0 == nullptr || (gamma && beta && (C1 == 0 || st1)),
+                 "gn_act_split: statistics need gamma, beta and (for a concatenated input) both halves");
+    DSEP_REQUIRE(act == 0 || act == 1, "gn_act_split: act must be 0 or 1");
+    DSEP_REQUIRE(B > 0 && P > 0 && B <= 65535, "gn_act_split: empty tensor");
+    if (st0 == nullptr) groups = 1;
+    int rc = check_gn_shape("gn_act_split", C0, C1, groups);
+    if (rc) return rc;
+    const int ppb = pix_per_block_for(P, B);
+    dim3 grid(ceil_div(P, ppb), B);
+    const size_t smem = sizeof(float) * (2 * (C0 + C1) + 128);
+    gn_act_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+        x0, C0, st0, x1, C1, st1, P, groups, gamma, beta, eps, act, (f16x4*)a_hi, (f16x4*)a_lo, (f16x4*)r_hi,
+        (f16x4*)r_lo, ppb);
     return check_launch("gn_act_split_kernel");
 }
 
+template <int MODE>
+static int launch_fir_tile(const float* x, int B, int H, int W, int C, int groups, const double* st,
+                           const float* gamma, const float* beta, float eps, void* a_hi, void* a_lo,
+                           void* r_hi, void* r_lo, float* y, cudaStream_t s) {
+    using FT = FirTile<MODE>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fir_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             FT::kSmemBytes);
+        if (e != cudaSuccess) {
+            set_error("fir_resample: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return DSEP_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int Ho = MODE == 1 ? H * 2 : H / 2, Wo = MODE == 1 ? W * 2 : W / 2;
+    const int tiles_w = ceil_div(Wo, FT::OW), tiles_h = ceil_div(Ho, FT::OH);
+    dim3 grid(tiles_w * tiles_h, C / 32, B);
+    fir_tile_kernel<MODE><<<grid, 256, FT::kSmemBytes, s>>>(x, H, W, C, groups, st, gamma, beta, eps, (f16x4*)a_hi,
+                                                            (f16x4*)a_lo, (f16x4*)r_hi, (f16x4*)r_lo, (float4*)y,
+                                                            tiles_w, tiles_h);
+    return check_launch("fir_tile_kernel");
+}
+
 extern "C" int dsep_fir_resample(const float* x, int B, int H, int W, int C, int mode, int groups,
-                                 const double* stats, const float* gamma, const float* beta, float eps,
+                                 const double* st, const float* gamma, const float* beta, float eps,
                                  void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y,
                                  dsep_stream_t stream) {
     DSEP_REQUIRE(x, "fir_resample: null input");
     DSEP_REQUIRE(mode == 1 || mode == 2, "fir_resample: mode must be 1 (up) or 2 (down)");
-    DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "fir_resample: empty tensor");
+    DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && B <= 65535, "fir_resample: empty tensor");
     DSEP_REQUIRE(mode == 1 || (H % 2 == 0 && W % 2 == 0), "fir_resample: down needs even H, W");
     DSEP_REQUIRE(a_hi || r_hi || y, "fir_resample: no output requested");
     cudaStream_t s = (cudaStream_t)stream;
     const int Ho = mode == 1 ? H * 2 : H / 2, Wo = mode == 1 ? W * 2 : W / 2;
-    if (C % 4 != 0) {
-        DSEP_REQUIRE(!a_hi && !r_hi && y, "fir_resample: C %% 4 != 0 supports the fp32 output only");
+    if (C % 32 != 0) {
+        DSEP_REQUIRE(!a_hi && !r_hi && y, "fir_resample: C %% 32 != 0 supports the fp32 output only");
         const int64_t total = (int64_t)B * Ho * Wo * C;
         if (mode == 1) fir_scalar_kernel<1><<<grid_for(total), 256, 0, s>>>(x, total, H, W, C, y);
         else fir_scalar_kernel<2><<<grid_for(total), 256, 0, s>>>(x, total, H, W, C, y);
@@ -422,20 +531,13 @@ extern "C" int dsep_fir_resample(const float* x, int B, int H, int W, int C, int
     }
     DSEP_REQUIRE((a_hi == nullptr) == (a_lo == nullptr) && (r_hi == nullptr) == (r_lo == nullptr),
                  "fir_resample: hi/lo planes must come in pairs");
-    if (stats) {
+    if (st) {
         DSEP_REQUIRE(gamma && beta && a_hi, "fir_resample: GroupNorm branch needs gamma, beta and a_hi/a_lo");
         int rc = check_gn_shape("fir_resample", C, 0, groups);
         if (rc) return rc;
     }
-    const int ppb = pix_per_block_for(Ho * Wo, B);
-    dim3 grid(ceil_div(Ho * Wo, ppb), B);
-    if (mode == 1)
-        fir_quad_kernel<1><<<grid, 256, 0, s>>>(x, H, W, C, groups, stats, gamma, beta, eps, (f16x4*)a_hi,
-                                                (f16x4*)a_lo, (f16x4*)r_hi, (f16x4*)r_lo, (float4*)y, ppb);
-    else
-        fir_quad_kernel<2><<<grid, 256, 0, s>>>(x, H, W, C, groups, stats, gamma, beta, eps, (f16x4*)a_hi,
-                                                (f16x4*)a_lo, (f16x4*)r_hi, (f16x4*)r_lo, (float4*)y, ppb);
-    return check_launch("fir_quad_kernel");
+    return mode == 1 ? launch_fir_tile<1>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, s)
+                     : launch_fir_tile<2>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, s);
 }
 
 extern "C" int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_x, int up_y, int down_x,

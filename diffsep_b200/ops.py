@@ -69,24 +69,33 @@ def split_f16(x, out: Split, prescale=1.0):
 
 
 def conv2d_tc(a: Split, B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store, bias=None, film=None,
-              film_stride=0, residual=None, scale=1.0, acc_scale=1.0, passes=3):
+              film_stride=0, residual=None, scale=1.0, acc_scale=1.0, passes=3, a2: Split = None, Cin2=0,
+              w2: Split = None, stats=None):
     _f32(out, "out"); _f32(bias, "bias"); _f32(film, "film"); _f32(residual, "residual")
+    if stats is not None and stats.dtype != torch.float64:
+        raise ValueError("stats must be float64 [B, C, 2]")
     call("dsep_conv2d_tc", ptr(a.hi), ptr(a.lo), B, H, W, Cin, ptr(w.hi), ptr(w.lo), cout_pad, ksize,
-         ptr(bias), film.data_ptr() if film is not None else None, film_stride, ptr(residual),
-         scale, acc_scale, ptr(out), cout_store, passes, stream())
+         ptr(a2.hi) if a2 else None, ptr(a2.lo) if a2 else None, Cin2, ptr(w2.hi) if w2 else None,
+         ptr(w2.lo) if w2 else None, ptr(bias), film.data_ptr() if film is not None else None, film_stride,
+         ptr(residual), scale, acc_scale, ptr(out), cout_store, ptr(stats), passes, stream())
     return out
 
 
-def gn_stats(x0, C0, x1, C1, B, P, groups, stats):
+def channel_stats(x, Cc, B, P, stats):
     if stats.dtype != torch.float64:
-        raise ValueError("stats must be float64 [B, groups, 2]")
-    call("dsep_gn_stats", ptr(_f32(x0, "x0")), C0, ptr(_f32(x1, "x1")), C1, B, P, groups, ptr(stats), stream())
+        raise ValueError("stats must be float64 [B, C, 2]")
+    call("dsep_channel_stats", ptr(_f32(x, "x")), Cc, B, P, ptr(stats), stream())
     return stats
 
 
-def gn_act_split(x0, C0, x1, C1, B, P, groups, stats, gamma, beta, eps, act, a: Split = None, r: Split = None):
-    call("dsep_gn_act_split", ptr(x0), C0, ptr(x1), C1, B, P, groups, ptr(stats), ptr(gamma), ptr(beta), eps,
-         act, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
+def zero(t):
+    call("dsep_zero", ptr(t), t.numel() * t.element_size(), stream())
+    return t
+
+
+def gn_act_split(x0, C0, st0, x1, C1, st1, B, P, groups, gamma, beta, eps, act, a: Split = None, r: Split = None):
+    call("dsep_gn_act_split", ptr(x0), C0, ptr(st0), ptr(x1), C1, ptr(st1), B, P, groups, ptr(gamma), ptr(beta),
+         eps, act, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
          ptr(r.lo) if r else None, stream())
 
 

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 1
+#define DSEP_ABI_VERSION 2
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -41,22 +41,28 @@ int dsep_abi_version(void);
 int dsep_device_ok(void);
 
 /* ---- tensor-core convolution -------------------------------------------------------------
- * out[b,h,w,n] = scale * ( acc_scale * sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c] + bias[n]
- *                          + film[b,n] + residual[b,h,w,n] )
+ * out[b,h,w,n] = scale * ( acc_scale * ( sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c]
+ *                                        + sum_c A2[b,h,w,c] * W2[n,c] )
+ *                          + bias[n] + film[b,n] + residual[b,h,w,n] )
+ * stats[b,n,0..1] += (sum, sum of squares) of out[b,:,:,n]                       (if stats != NULL)
  * Implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators).  ksize 3 (pad 1) or 1.  A is a split
  * tensor [B,H,W,Cin] (Cin % 64 == 0); Wt a split tensor [ksize*ksize, Cout_pad, Cin] with
  * Cout_pad in {16} or a multiple of 64; only the first cout_store channels are written, with
- * row pitch cout_store.  passes = 3: hi*hi + lo*hi + hi*lo (fp32-grade); passes = 1: hi*hi
- * (11-bit operands, TF32-grade).  acc_scale undoes the power-of-two pre-scaling that keeps the
- * fp16 weight planes in the normal range (Wt holds w / acc_scale).
- * bias/film/residual may be NULL.  film is [B, film_stride] (pointer already offset to this
- * layer's first channel).
+ * row pitch cout_store.  A2 [B,H,W,Cin2] / W2 [Cout_pad, Cin2] (Cin2 = 0: none) is a fused 1x1
+ * convolution accumulated into the same tile (the ResBlock shortcut Conv_2).
+ * passes = 3: hi*hi + lo*hi + hi*lo (fp32-grade); passes = 1: hi*hi (11-bit operands, TF32-grade).
+ * acc_scale undoes the power-of-two pre-scaling that keeps the fp16 weight planes in the normal
+ * range (Wt and W2 hold w / acc_scale).  bias/film/residual may be NULL.  film is [B, film_stride]
+ * (pointer already offset to this layer's first channel).  stats is double [B, cout_store, 2],
+ * accumulated atomically (zero it first; needs Cout >= 64 and a map of at least 128 pixels).
  * Replaces nn.Conv2d -> cuDNN in ddpm_conv3x3/ddpm_conv1x1 (models/ncsnpp_utils/layers.py:112-156),
- * NIN (layers.py:678-689), Dense_0 bias add and the (x+h)/sqrt(2) residual (layerspp.py:311-323). */
+ * NIN (layers.py:678-689), Dense_0 bias add, Conv_2 shortcut and the (x+h)/sqrt(2) residual
+ * (layerspp.py:311-323), and the reduction half of the following nn.GroupNorm. */
 int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
                    const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
+                   const void* a2_hi, const void* a2_lo, int Cin2, const void* w2_hi, const void* w2_lo,
                    const float* bias, const float* film, int film_stride, const float* residual,
-                   float scale, float acc_scale, float* out, int cout_store, int passes,
+                   float scale, float acc_scale, float* out, int cout_store, double* stats, int passes,
                    dsep_stream_t stream);
 
 /* x * prescale (fp32, n elements) -> split fp16 planes. */
@@ -64,24 +70,29 @@ int dsep_split_f16(const float* x, int64_t n, float prescale, void* hi, void* lo
                    dsep_stream_t stream);
 
 /* ---- GroupNorm / SiLU / FIR resampling ------------------------------------------------------
- * Channel-concatenated input [x0 (C0 ch) | x1 (C1 ch)] (x1 may be NULL, C1 = 0), pixels P=H*W.
- * stats is double [B, groups, 2] = (sum, sum of squares), zeroed and filled by dsep_gn_stats.
+ * GroupNorm statistics travel as per-channel sums: double [B, C, 2] = (sum, sum of squares) over the
+ * P = H*W pixels, produced by dsep_conv2d_tc's epilogue or by dsep_channel_stats; consumers
+ * combine them per group, so a channel-concatenated input [x0 (C0 ch) | x1 (C1 ch)] (x1 may be
+ * NULL, C1 = 0) needs no pass of its own.
  * Replaces nn.GroupNorm(min(C//4,32), eps=1e-6) + nn.SiLU (layerspp.py:264-266,292; ncsnpp.py:253-258)
  * and torch.cat([h, hs.pop()]) (ncsnpp.py:411). */
-int dsep_gn_stats(const float* x0, int C0, const float* x1, int C1, int B, int P, int groups,
-                  double* stats, dsep_stream_t stream);
+int dsep_channel_stats(const float* x, int C, int B, int P, double* stats, dsep_stream_t stream);
+/* memset(ptr, 0, bytes) on the stream (zeroing the statistics arena before an evaluation). */
+int dsep_zero(void* ptr, int64_t bytes, dsep_stream_t stream);
 /* a = act(GN(x)) as split planes (act: 0 none, 1 SiLU); optionally also the raw x as split
- * planes (r_hi/r_lo, for the 1x1 shortcut conv) — all in the concatenated channel layout. */
-int dsep_gn_act_split(const float* x0, int C0, const float* x1, int C1, int B, int P, int groups,
-                      const double* stats, const float* gamma, const float* beta, float eps, int act,
-                      void* a_hi, void* a_lo, void* r_hi, void* r_lo, dsep_stream_t stream);
+ * planes (r_hi/r_lo, for the 1x1 shortcut conv) — all in the concatenated channel layout.
+ * st0/st1 NULL => no GroupNorm (plain split). */
+int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x1, int C1,
+                      const double* st1, int B, int P, int groups, const float* gamma, const float* beta,
+                      float eps, int act, void* a_hi, void* a_lo, void* r_hi, void* r_lo,
+                      dsep_stream_t stream);
 /* 2x FIR resampling with taps [1,3,3,1] of an fp32 [B,H,W,C] tensor (mode 1: up, 2: down).
  * Outputs (each nullable pair): a = FIR(act(GN(x))) split, r = FIR(x) split, y = FIR(x) fp32.
- * stats/gamma/beta NULL => no GroupNorm branch.
+ * st/gamma/beta NULL => no GroupNorm branch.
  * Replaces upsample_2d/downsample_2d (models/ncsnpp_utils/up_or_down_sampling.py:206-273)
  * -> upfirdn2d (op/upfirdn2d.py:145-156, upfirdn2d_kernel.cu:107-369). */
 int dsep_fir_resample(const float* x, int B, int H, int W, int C, int mode, int groups,
-                      const double* stats, const float* gamma, const float* beta, float eps,
+                      const double* st, const float* gamma, const float* beta, float eps,
                       void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y, dsep_stream_t stream);
 /* Drop-in for the reference's own FFI signature on its own layout: in [planes, H, W] fp32,
  * kernel fixed to outer([1,3,3,1])/16*up^2; supports exactly the two calls the model makes
