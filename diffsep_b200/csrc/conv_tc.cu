@@ -193,6 +193,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int ew = warp - 4;
         const int wq = ew & 3;                // TMEM lane quarter == warp_id % 4
         const int tw_mask = (1 << p.tw_log2) - 1, th_mask = (1 << p.th_log2) - 1;
+        // GroupNorm partial sums of this thread's 4 channels, carried across consecutive tiles of the
+        // same (batch entry, channel tile) and flushed with fp64 atomics only when that changes
+        float4 run1[NT >= 64 ? NT / 64 : 1], run2[NT >= 64 ? NT / 64 : 1];
+        int run_b = -1, run_n0 = -1;
+        auto flush_stats = [&]() {
+            if constexpr (NT >= 64) {
+                if (p.stats == nullptr || run_b < 0 || (lane >> 3) != 0) return;
+#pragma unroll
+                for (int c = 0; c < NT / 64; ++c) {
+                    const int n = run_n0 + (ew >> 2) * (NT / 2) + c * 32 + (lane & 7) * 4;
+                    if (n < p.cout_store) {
+                        double* st = p.stats + (static_cast<size_t>(run_b) * p.cout_store + n) * 2;
+                        atomicAdd(st + 0, (double)run1[c].x); atomicAdd(st + 1, (double)run2[c].x);
+                        atomicAdd(st + 2, (double)run1[c].y); atomicAdd(st + 3, (double)run2[c].y);
+                        atomicAdd(st + 4, (double)run1[c].z); atomicAdd(st + 5, (double)run2[c].z);
+                        atomicAdd(st + 6, (double)run1[c].w); atomicAdd(st + 7, (double)run2[c].w);
+                    }
+                }
+            }
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
@@ -203,29 +223,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int w0 = wt << p.tw_log2, h0 = ht << p.th_log2, b0 = r << tb_log2;
             const int n0 = nt * NT;
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 2 * NT;
+            if constexpr (NT >= 64) {
+                if (p.stats != nullptr && (b0 != run_b || n0 != run_n0)) {
+                    flush_stats();
+                    run_b = b0; run_n0 = n0;
+#pragma unroll
+                    for (int c = 0; c < NT / 64; ++c) run1[c] = run2[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
 
             if constexpr (NT >= 64) {
                 constexpr int kChunks = NT / 64;          // 32-column chunks per warp
                 const int chalf = ew >> 2;                // which half of the tile's columns
                 float* stg = staging + ew * (32 * 32);
                 const int q = lane & 7, rg = lane >> 3;
-                // pixel of each of this thread's 8 output rows (row = i*4 + rg of this warp's 32)
-                size_t pix_off[8];
-                int bsel[8];
-                uint32_t valid = 0;
+                // pixel of each of this thread's 8 output rows (row = i*4 + rg of this warp's 32);
+                // kNoPix marks rows outside the image / batch
+                constexpr uint32_t kNoPix = 0xFFFFFFFFu;
+                uint32_t pix[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int m = wq * 32 + i * 4 + rg;
                     const int w = w0 + (m & tw_mask);
                     const int h = h0 + ((m >> p.tw_log2) & th_mask);
                     const int b = b0 + (m >> (p.tw_log2 + p.th_log2));
-                    const bool ok = b < p.B && h < p.H && w < p.W;
-                    valid |= (ok ? 1u : 0u) << i;
-                    bsel[i] = ok ? b : 0;
-                    pix_off[i] = ok ? ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.cout_store : 0;
+                    pix[i] = (b < p.B && h < p.H && w < p.W) ? static_cast<uint32_t>((b * p.H + h) * p.W + w) : kNoPix;
                 }
                 bool waited = false;
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
                     const int col0 = chalf * (NT / 2) + c * 32;
                     const int n = n0 + col0 + q * 4;
@@ -235,8 +260,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     if (p.residual != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            res[i] = (n_ok && ((valid >> i) & 1u))
-                                         ? __ldg(reinterpret_cast<const float4*>(p.residual + pix_off[i] + n))
+                            res[i] = (n_ok && pix[i] != kNoPix)
+                                         ? __ldg(reinterpret_cast<const float4*>(
+                                               p.residual + static_cast<size_t>(pix[i]) * p.cout_store + n))
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (!waited) {
@@ -246,12 +272,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     }
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + col0, v);
-                    if (three) {
-                        uint32_t u[32];
-                        tmem_ld_32x32(t_addr + NT + col0, u);
-                        tmem_ld_wait();
+                    if (three) {   // add the hi*lo half, 16 columns at a time (register pressure)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t u[16];
+                            tmem_ld_32x16(t_addr + NT + col0 + hh * 16, u);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                v[hh * 16 + j] = __float_as_uint(__uint_as_float(v[hh * 16 + j]) + __uint_as_float(u[j]));
+                        }
                     } else {
                         tmem_ld_wait();
                     }
@@ -273,20 +303,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = i * 4 + rg;
-                        if (n_ok && ((valid >> i) & 1u)) {
+                        if (n_ok && pix[i] != kNoPix) {
                             float4 a = *reinterpret_cast<const float4*>(stg + row * 32 + ((q ^ (row & 7)) << 2));
                             a.x = fmaf(a.x, p.acc_scale, bz.x); a.y = fmaf(a.y, p.acc_scale, bz.y);
                             a.z = fmaf(a.z, p.acc_scale, bz.z); a.w = fmaf(a.w, p.acc_scale, bz.w);
                             if (p.film != nullptr) {
+                                const int bi = b0 + ((wq * 32 + row) >> (p.tw_log2 + p.th_log2));
                                 const float4 f = __ldg(reinterpret_cast<const float4*>(
-                                    p.film + static_cast<size_t>(bsel[i]) * p.film_stride + n));
+                                    p.film + static_cast<size_t>(bi) * p.film_stride + n));
                                 a.x += f.x; a.y += f.y; a.z += f.z; a.w += f.w;
                             }
                             if (p.residual != nullptr) {
                                 a.x += res[i].x; a.y += res[i].y; a.z += res[i].z; a.w += res[i].w;
                             }
                             a.x *= p.scale; a.y *= p.scale; a.z *= p.scale; a.w *= p.scale;
-                            *reinterpret_cast<float4*>(p.out + pix_off[i] + n) = a;
+                            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(pix[i]) * p.cout_store + n) = a;
                             s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
                             s2.x = fmaf(a.x, a.x, s2.x); s2.y = fmaf(a.y, a.y, s2.y);
                             s2.z = fmaf(a.z, a.z, s2.z); s2.w = fmaf(a.w, a.w, s2.w);
@@ -301,13 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
                             s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
                         }
-                        if (rg == 0 && n_ok && b0 < p.B) {
-                            double* st = p.stats + (static_cast<size_t>(b0) * p.cout_store + n) * 2;
-                            atomicAdd(st + 0, (double)s1.x); atomicAdd(st + 1, (double)s2.x);
-                            atomicAdd(st + 2, (double)s1.y); atomicAdd(st + 3, (double)s2.y);
-                            atomicAdd(st + 4, (double)s1.z); atomicAdd(st + 5, (double)s2.z);
-                            atomicAdd(st + 6, (double)s1.w); atomicAdd(st + 7, (double)s2.w);
-                        }
+                        run1[c].x += s1.x; run1[c].y += s1.y; run1[c].z += s1.z; run1[c].w += s1.w;
+                        run2[c].x += s2.x; run2[c].y += s2.y; run2[c].z += s2.z; run2[c].w += s2.w;
                     }
                     __syncwarp();
                 }
@@ -350,6 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 }
             }
         }
+        flush_stats();
     }
 
     tc_fence_before();

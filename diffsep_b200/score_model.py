@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 
 import torch
 
@@ -93,6 +94,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self._bufs = {}
         self._mix_cache = None     # (data_ptr, B, T) of the mixture whose spectrogram is resident
         self._mix_cache_on = False
+        self.use_cuda_graph = bool(int(os.environ.get("DSEP_CUDA_GRAPH", "1")))
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -106,6 +108,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
             self.window = state_dict["stft.window"].detach().to(self.dev, torch.float32).contiguous()
         self.backbone = NCSNppB200(bb, nf=self.nf, ch_in=self.ch_in, ch_out=self.ch_out, device=self.dev,
                                    passes=self.passes)
+        self._bufs = {}        # drops captured graphs that reference the old weights
         return self
 
     # -------------------------------------------------------------- buffers per (B, T)
@@ -157,28 +160,58 @@ class ScoreModelNCSNpp(torch.nn.Module):
         time = time.contiguous().float()
         bf = self._work(B, T)
         Fr, Wp = bf["Fr"], bf["Wp"]
-        Ctot = ns + 1
 
         mix_key = (mix.data_ptr(), B, T)
-        if not (self._mix_cache_on and self._mix_cache == mix_key):
+        if self._mix_cache_on and self._mix_cache == mix_key:
+            if self.use_cuda_graph:
+                return self._replay(xt, time, bf)
+        else:
             ops.stft_frames(mix, self.window, B, 1, T, Fr, bf["frames_mix"])
             ops.sgemm(bf["frames_mix"], LD, self.basis_fwd, LD, bf["dft_mix"], LD, B * Fr, LD, LD)
-            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, Ctot, 64, self.spec_factor, self.spec_abs_exponent,
+            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, ns + 1, 64, self.spec_factor, self.spec_abs_exponent,
                           bf["x_pyr"], bf["x_planes"])
             self._mix_cache = mix_key if self._mix_cache_on else None
+        return self._evaluate(xt, time, bf)
+
+    def _evaluate(self, xt, time, bf):
+        """Everything that depends on xt / t: the launch sequence one CUDA graph captures."""
+        B, ns, T = xt.shape
+        Fr, Wp = bf["Fr"], bf["Wp"]
         ops.stft_frames(xt, self.window, B, ns, T, Fr, bf["frames"])
         ops.sgemm(bf["frames"], LD, self.basis_fwd, LD, bf["dft"], LD, B * ns * Fr, LD, LD)
-        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, Ctot, 64, self.spec_factor, self.spec_abs_exponent,
+        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, 64, self.spec_factor, self.spec_abs_exponent,
                       bf["x_pyr"], bf["x_planes"])
-
         pyr = self.backbone(bf["x_planes"], bf["x_pyr"], time)
-
         ops.out_head(pyr, B, Wp, self.ch_in, ns, Fr, time, self.backbone.out_w, self.backbone.out_b,
                      self.spec_factor, self.spec_abs_exponent, bf["spec_out"])
         ops.sgemm(bf["spec_out"], LD, self.basis_inv, LD, bf["frames_out"], LD, B * ns * Fr, LD, LD)
         out = torch.empty(B, ns, T, device=self.dev, dtype=torch.float32)
         ops.istft_ola(bf["frames_out"], self.window, B, ns, Fr, T, out)
         return out
+
+    def _replay(self, xt, time, bf):
+        """Inside a sampling run (mixture spectrogram resident) the ~300 launches of one evaluation
+        are replayed from a CUDA graph: static input buffers, one graph launch per evaluation."""
+        from . import _lib
+        g = bf.get("graph")
+        if g is None:
+            B, ns, T = xt.shape
+            xs = torch.empty_like(xt)
+            ts = torch.empty_like(time)
+            xs.copy_(xt); ts.copy_(time)
+            self._evaluate(xs, ts, bf)                 # warm-up outside capture: plans, attributes
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.N_CALLS
+            with torch.cuda.graph(graph):
+                out = self._evaluate(xs, ts, bf)
+            g = bf["graph"] = (graph, xs, ts, out, _lib.N_CALLS - n0)
+        graph, xs, ts, out, n_launches = g
+        xs.copy_(xt)
+        ts.copy_(time)
+        graph.replay()
+        _lib.N_CALLS += n_launches
+        return out.clone()
 
 
 # NCSNpp constructor defaults (reference models/ncsnpp.py:45-70): anything else is not on the hot path
