@@ -51,7 +51,7 @@ PROTOTYPES = {
     "dsep_scale_output": [_p, _p, _i, _i, _i, _p, _p],
     "dsep_randn": [_p, _i64, _u64, _u64, _p],
 }
-OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok")
+OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok", "dsep_conv_kblock")
 
 _lib = None
 
@@ -74,6 +74,7 @@ def load():
     lib.dsep_last_error.argtypes = []
     lib.dsep_abi_version.restype = C.c_int
     lib.dsep_device_ok.restype = C.c_int
+    lib.dsep_conv_kblock.restype = C.c_int
     if lib.dsep_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libdsep.so ABI {lib.dsep_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = lib

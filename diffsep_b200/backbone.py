@@ -37,6 +37,12 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def cin_align():
+    """channel granularity of tensor-core operands (the conv kernel's K-block)"""
+    from . import _lib
+    return _lib.load().dsep_conv_kblock()
+
+
 def gn_groups(c):
     return min(c // 4, 32)
 
@@ -57,7 +63,7 @@ class ConvWeight:
         cout, cin, kh, kw = w.shape
         assert kh == kw and kh in (1, 3)
         self.ksize, self.cout, self.cin = kh, cout, cin
-        self.cin_pad = _round_up(cin, 64)
+        self.cin_pad = _round_up(cin, cin_align())
         self.cout_pad = 16 if cout <= 16 else _round_up(cout, 64)
         wt = torch.zeros(kh * kw, self.cout_pad, self.cin_pad, device=device, dtype=torch.float32)
         wt[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
@@ -67,7 +73,7 @@ class ConvWeight:
             w2 = shortcut[0].detach().to(device=device, dtype=torch.float32)
             assert w2.shape[0] == cout and w2.shape[2:] == (1, 1)
             self.cin2 = w2.shape[1]
-            self.cin2_pad = _round_up(self.cin2, 64)
+            self.cin2_pad = _round_up(self.cin2, cin_align())
             w2t = torch.zeros(self.cout_pad, self.cin2_pad, device=device, dtype=torch.float32)
             w2t[:cout, :self.cin2] = w2.reshape(cout, self.cin2)
             amax = max(amax, float(w2t.abs().max()))
@@ -249,7 +255,7 @@ class NCSNppB200:
         return self._plans[key]
 
     def __call__(self, x_planes: Split, x_pyramid, t):
-        """x_planes: split [B,256,W,64] network input (2x-1 applied, channels >= ch_in zero);
+        """x_planes: split [B,256,W,conv_in.cin_pad] network input (2x-1 applied, channels >= ch_in zero);
         x_pyramid: the same input as fp32 [B,256,W,ch_in]; t: [B].  Returns the output pyramid
         [B,256,W,ch_in] fp32 (before the /t scaling and the output 1x1 conv, which
         ``dsep_out_head`` fuses with the spectrogram decompression)."""

@@ -57,6 +57,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred P;\n\t"
@@ -89,6 +90,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         " [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// multicast variant: the box lands at the same CTA-relative smem offset, and completes on the mbarrier at
+// the same offset, in every CTA of the cluster selected by cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---- tcgen05 / TMEM
@@ -124,6 +146,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                      smem_u32(bar))
                  : "memory");
 }
+// same, arriving on the barrier at this offset in every CTA of cta_mask (frees a multicast-fed slot)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i gets TMEM lane (base_lane + i).
@@ -158,6 +187,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride between 8-row groups
     d |= 1ull << 46;                                         // descriptor version (sm_100)
     d |= 2ull << 61;                                         // SWIZZLE_128B
+    return d;
+}
+// Same for 64-byte-swizzled operands (32 fp16 of K per row; 8-row x 64 B atoms, 512 B apart).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 4ull << 61;                                         // SWIZZLE_64B
     return d;
 }
 // Instruction descriptor (kind::f16): fp16 x fp16 -> fp32 (c_format = 1 at bit 4, a/b_format = 0

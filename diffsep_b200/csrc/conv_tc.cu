@@ -32,6 +32,8 @@
 //     transpose (conflict-free both ways) -> bias/FiLM/residual/scale fused -> 128-byte
 //     coalesced fp32 stores; per-channel (sum, sum^2) reduced in registers + 2 shuffles and
 //     accumulated with fp64 atomics.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -42,9 +44,9 @@ struct ConvParams {
     int B, H, W, Cin, Cout_pad, cout_store;
     int taps;              // 1 or 9
     int tw_log2, th_log2;  // pixel tile: tw x th x tb = 128
-    int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
-    int kblocks;           // Cin / 64
-    int kblocks2;          // Cin2 / 64 of the fused 1x1 shortcut (0: none)
+    int tiles_w, tiles_h, tiles_b, tiles_n, total_items;   // item = (pair of M-adjacent tiles, channel tile)
+    int kblocks;           // Cin / kBK
+    int kblocks2;          // Cin2 / kBK of the fused 1x1 shortcut (0: none)
     int passes;            // 1 or 3
     const float* bias;
     const float* film;
@@ -53,24 +55,39 @@ struct ConvParams {
     float scale, acc_scale;
     float* out;
     double* stats;         // [B, cout_store, 2] or null
+    int debug;             // DSEP_CONV_DEBUG bitmask: 1 skip MMA issue, 2 skip TMA loads, 4 skip epilogue stores (timing experiments)
 };
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
+// K-block: channels per pipeline stage.  64 (128-byte swizzle) is the default; 32 (64-byte swizzle,
+// twice as many half-size stages) was measured 16 % slower: the operand feed is bound by L2->SM
+// delivery (~12.6 TB/s with 128-byte rows, ~7 TB/s with 64-byte rows), not by ring depth.
+#ifndef DSEP_CONV_BK
+#define DSEP_CONV_BK 64
+#endif
+constexpr int kBK = DSEP_CONV_BK;
+static_assert(kBK == 32 || kBK == 64, "K-block must be 32 or 64 channels");
+constexpr int kABytes = 128 * kBK * 2;     // one A plane of a stage
 
 template <int NT>
 struct ConvCfg {
-    static constexpr int kStageBytes = 2 * 16384 + 2 * NT * 128;
+    static constexpr int kBBytes = NT * kBK * 2;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kStagingBytes = NT >= 64 ? kEpiWarps * 32 * 32 * 4 : 0;
-    static constexpr int kAvail = 232448 - 1024 - 256 - kStagingBytes;
+    static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes;
     static constexpr int kStagesMax = kAvail / kStageBytes;
-    static constexpr int kStages = kStagesMax > 6 ? 6 : kStagesMax;
+    static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
     static constexpr int kTmemCols = 4 * NT < 32 ? 32 : 4 * NT;   // 2 stages x (hi*hi+lo*hi | hi*lo)
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 + 1024;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 512 + 1024;
 };
 
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
+    return kBK == 64 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
+}
+
 template <int NT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
@@ -92,6 +109,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const bool three = p.passes == 3;
+    // CTA pair: the two CTAs of a cluster work on M-adjacent tiles of the same channel tile, each
+    // fetches half of every weight tile and multicasts it to both (halves the weight traffic)
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi);
@@ -102,7 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NS; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], 2);    // one tcgen05.commit from each CTA of the pair
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -113,22 +134,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();          // both CTAs' barriers are initialised before any multicast targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     const int tb_log2 = 7 - p.tw_log2 - p.th_log2;
     const int kiters = p.taps * p.kblocks + p.kblocks2;
-    const uint32_t stage_tx = (three ? 2u : 1u) * (16384u + NT * 128u);
+    const uint32_t stage_tx = (three ? 2u : 1u) * static_cast<uint32_t>(kABytes + Cfg::kBBytes);
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            int r = tile;
-            const int nt = r % p.tiles_n; r /= p.tiles_n;
+        for (int item = cluster_id; item < p.total_items; item += num_clusters) {
+            const int nt = item % p.tiles_n;
+            int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);      // this CTA's M tile of the pair
             const int wt = r % p.tiles_w; r /= p.tiles_w;
             const int ht = r % p.tiles_h; r /= p.tiles_h;
+            // r >= tiles_b only for the odd tile out of the last pair: b0 >= B, so TMA zero-fills
+            // and every store is masked
             const int w0 = wt << p.tw_log2, h0 = ht << p.th_log2, b0 = r << tb_log2;
             const int n0 = nt * NT;
             for (int ki = 0; ki < kiters; ++ki) {
@@ -143,14 +167,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 }
                 mbar_wait(&empty[stage], phase ^ 1u);
                 uint8_t* s = stage_base + stage * Cfg::kStageBytes;
+                if (p.debug & 2) {
+                    mbar_arrive(&full[stage]);
+                    if (++stage == NS) { stage = 0; phase ^= 1u; }
+                    continue;
+                }
                 mbar_arrive_expect_tx(&full[stage], stage_tx);
                 const int wrow = second ? n0 : tap * p.Cout_pad + n0;
-                tma_load_4d(s, second ? &tm_a2_hi : &tm_a_hi, &full[stage], kb * 64, w0 + dx, h0 + dy, b0);
-                tma_load_2d(s + 32768, second ? &tm_w2_hi : &tm_w_hi, &full[stage], kb * 64, wrow);
+                const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);        // my half of the weight rows
+                const int boff = static_cast<int>(rank) * (Cfg::kBBytes / 2);
+                tma_load_4d(s, second ? &tm_a2_hi : &tm_a_hi, &full[stage], kb * kBK, w0 + dx, h0 + dy, b0);
+                tma_load_2d_mc(s + 2 * kABytes + boff, second ? &tm_w2_hi : &tm_w_hi, &full[stage], kb * kBK,
+                               wrow_h, 0x3);
                 if (three) {
-                    tma_load_4d(s + 16384, second ? &tm_a2_lo : &tm_a_lo, &full[stage], kb * 64, w0 + dx,
+                    tma_load_4d(s + kABytes, second ? &tm_a2_lo : &tm_a_lo, &full[stage], kb * kBK, w0 + dx,
                                 h0 + dy, b0);
-                    tma_load_2d(s + 32768 + NT * 128, second ? &tm_w2_lo : &tm_w_lo, &full[stage], kb * 64, wrow);
+                    tma_load_2d_mc(s + 2 * kABytes + Cfg::kBBytes + boff, second ? &tm_w2_lo : &tm_w_lo,
+                                   &full[stage], kb * kBK, wrow_h, 0x3);
                 }
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
@@ -162,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
             const int as = it & 1;
             mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
             tc_fence_after();
@@ -172,18 +205,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 tc_fence_after();
                 const uint32_t s = smem_u32(stage_base + stage * Cfg::kStageBytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t a_hi = umma_desc_sw128(s + k * 32);
-                    const uint64_t b_hi = umma_desc_sw128(s + 32768 + k * 32);   // W_hi rows, then W_lo rows
+                for (int k = 0; k < kBK / 16; ++k) {
+                    if (p.debug & 1) break;
+                    const uint64_t a_hi = umma_desc_k(s + k * 32);
+                    const uint64_t b_hi = umma_desc_k(s + 2 * kABytes + k * 32);   // W_hi rows, then W_lo rows
                     if (three) {
                         umma_f16(d_tmem, a_hi, b_hi, idesc_2n, (ki | k) != 0);
-                        const uint64_t a_lo = umma_desc_sw128(s + 16384 + k * 32);
+                        const uint64_t a_lo = umma_desc_k(s + kABytes + k * 32);
                         umma_f16(d_tmem, a_lo, b_hi, idesc_n, 1);
                     } else {
                         umma_f16(d_tmem, a_hi, b_hi, idesc_n, (ki | k) != 0);
                     }
                 }
-                umma_commit(&empty[stage]);   // frees the smem slot once these MMAs retire
+                umma_commit_mc(&empty[stage], 0x3);   // frees this slot in BOTH CTAs once these MMAs retire
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
             umma_commit(&tfull[as]);          // accumulator complete -> epilogue
@@ -199,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         int run_b = -1, run_n0 = -1;
         auto flush_stats = [&]() {
             if constexpr (NT >= 64) {
-                if (p.stats == nullptr || run_b < 0 || (lane >> 3) != 0) return;
+                if (p.stats == nullptr || run_b < 0 || run_b >= p.B || (lane >> 3) != 0) return;
 #pragma unroll
                 for (int c = 0; c < NT / 64; ++c) {
                     const int n = run_n0 + (ew >> 2) * (NT / 2) + c * 32 + (lane & 7) * 4;
@@ -214,12 +248,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
         };
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
             const int as = it & 1;
-            int r = tile;
-            const int nt = r % p.tiles_n; r /= p.tiles_n;
+            const int nt = item % p.tiles_n;
+            int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);      // this CTA's M tile of the pair
             const int wt = r % p.tiles_w; r /= p.tiles_w;
             const int ht = r % p.tiles_h; r /= p.tiles_h;
+            // r >= tiles_b only for the odd tile out of the last pair: b0 >= B, so TMA zero-fills
+            // and every store is masked
             const int w0 = wt << p.tw_log2, h0 = ht << p.th_log2, b0 = r << tb_log2;
             const int n0 = nt * NT;
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 2 * NT;
@@ -317,7 +353,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                                 a.x += res[i].x; a.y += res[i].y; a.z += res[i].z; a.w += res[i].w;
                             }
                             a.x *= p.scale; a.y *= p.scale; a.z *= p.scale; a.w *= p.scale;
-                            *reinterpret_cast<float4*>(p.out + static_cast<size_t>(pix[i]) * p.cout_store + n) = a;
+                            if (!(p.debug & 4))
+                                *reinterpret_cast<float4*>(p.out + static_cast<size_t>(pix[i]) * p.cout_store + n) = a;
                             s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
                             s2.x = fmaf(a.x, a.x, s2.x); s2.y = fmaf(a.y, a.y, s2.y);
                             s2.z = fmaf(a.z, a.z, s2.z); s2.w = fmaf(a.w, a.w, s2.w);
@@ -381,6 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();          // the peer may still multicast into / arrive on this CTA's shared memory
     if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
@@ -405,6 +443,7 @@ static EncodeTiledFn get_encode_tiled() {
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    const CUtensorMapSwizzle swz = kBK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     EncodeTiledFn enc = get_encode_tiled();
     if (enc == nullptr) {
         set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
@@ -412,7 +451,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims,
-                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
@@ -448,7 +487,8 @@ static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stre
         set_error("cudaFuncSetAttribute(conv_tc_kernel<%d>): %s", NT, cudaGetErrorString(attr_err));
         return DSEP_ERR_CUDA;
     }
-    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    const int max_clusters = num_sms() / 2;
+    const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
     conv_tc_kernel<NT><<<grid, kThreads, ConvCfg<NT>::kSmemBytes, stream>>>(
         m.a_hi, m.a_lo, m.w_hi, m.w_lo, m.a2_hi, m.a2_lo, m.w2_hi, m.w2_lo, p);
     return check_launch("conv_tc_kernel");
@@ -462,6 +502,8 @@ static int ilog2(int v) {
 
 }  // namespace dsep
 
+extern "C" int dsep_conv_kblock(void) { return dsep::kBK; }
+
 extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
                               const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
                               const void* a2_hi, const void* a2_lo, int Cin2, const void* w2_hi,
@@ -474,12 +516,12 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     DSEP_REQUIRE(passes == 1 || (a_lo && w_lo), "conv2d_tc: passes=3 needs the lo planes");
     DSEP_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize must be 1 or 3 (got %d)", ksize);
     DSEP_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_tc: empty tensor");
-    DSEP_REQUIRE(Cin > 0 && Cin % 64 == 0, "conv2d_tc: Cin must be a multiple of 64 (got %d)", Cin);
+    DSEP_REQUIRE(Cin > 0 && Cin % kBK == 0, "conv2d_tc: Cin must be a multiple of %d (got %d)", kBK, Cin);
     DSEP_REQUIRE(Cout_pad == 16 || (Cout_pad > 0 && Cout_pad % 64 == 0),
                  "conv2d_tc: Cout_pad must be 16 or a multiple of 64 (got %d)", Cout_pad);
     DSEP_REQUIRE(cout_store > 0 && cout_store <= Cout_pad, "conv2d_tc: bad cout_store %d", cout_store);
     DSEP_REQUIRE(Cout_pad == 16 || cout_store % 4 == 0, "conv2d_tc: cout_store must be a multiple of 4");
-    DSEP_REQUIRE(Cin2 >= 0 && Cin2 % 64 == 0, "conv2d_tc: Cin2 must be a multiple of 64 (got %d)", Cin2);
+    DSEP_REQUIRE(Cin2 >= 0 && Cin2 % kBK == 0, "conv2d_tc: Cin2 must be a multiple of %d (got %d)", kBK, Cin2);
     DSEP_REQUIRE(Cin2 == 0 || (a2_hi && w2_hi && (passes == 1 || (a2_lo && w2_lo))),
                  "conv2d_tc: fused 1x1 operand (Cin2=%d) needs its activation and weight planes", Cin2);
     const int NT = Cout_pad == 16 ? 16 : (Cout_pad % 128 == 0 ? 128 : 64);
@@ -496,22 +538,26 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
     p.tiles_w = ceil_div(W, tw); p.tiles_h = ceil_div(H, th); p.tiles_b = ceil_div(B, tb);
     p.tiles_n = Cout_pad / NT;
-    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
-    p.kblocks = Cin / 64;
-    p.kblocks2 = Cin2 / 64;
+    p.total_items = ((p.tiles_w * p.tiles_h * p.tiles_b + 1) / 2) * p.tiles_n;
+    p.kblocks = Cin / kBK;
+    p.kblocks2 = Cin2 / kBK;
     p.passes = passes;
     p.bias = bias; p.film = film; p.film_stride = film_stride; p.residual = residual;
     p.scale = scale; p.acc_scale = acc_scale; p.out = out; p.stats = stats;
+    {
+        static const int dbg = getenv("DSEP_CONV_DEBUG") ? atoi(getenv("DSEP_CONV_DEBUG")) : 0;
+        p.debug = dbg;
+    }
 
     ConvMaps m;
     int rc;
     {
         const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        const cuuint32_t abox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+        const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
         const cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)p.taps * Cout_pad};
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
-        const cuuint32_t wbox[2] = {64, (cuuint32_t)NT};
+        const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
         if ((rc = make_map(&m.a_hi, a_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
         if ((rc = make_map(&m.w_hi, w_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         if (passes == 3) {
@@ -525,10 +571,10 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     if (Cin2 > 0) {
         const cuuint64_t adims[4] = {(cuuint64_t)Cin2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t astr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)W * Cin2 * 2, (cuuint64_t)H * W * Cin2 * 2};
-        const cuuint32_t abox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+        const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
         const cuuint64_t wdims[2] = {(cuuint64_t)Cin2, (cuuint64_t)Cout_pad};
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin2 * 2};
-        const cuuint32_t wbox[2] = {64, (cuuint32_t)NT};
+        const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
         if ((rc = make_map(&m.a2_hi, a2_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
         if ((rc = make_map(&m.w2_hi, w2_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         if (passes == 3) {

@@ -124,7 +124,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
             Fr=Fr, Wp=Wp,
             frames=f32(B * ns * Fr, LD), dft=f32(B * ns * Fr, LD),
             frames_mix=f32(B * Fr, LD), dft_mix=f32(B * Fr, LD),
-            x_planes=Split.zeros((B, N_BINS, Wp, 64), dev),
+            x_planes=Split.zeros((B, N_BINS, Wp, self.backbone.conv_in.cin_pad), dev),
             x_pyr=f32(B, N_BINS, Wp, self.ch_in),
             spec_out=f32(B * ns * Fr, LD), frames_out=f32(B * ns * Fr, LD),
             score=f32(B, ns, T),
@@ -168,7 +168,8 @@ class ScoreModelNCSNpp(torch.nn.Module):
         else:
             ops.stft_frames(mix, self.window, B, 1, T, Fr, bf["frames_mix"])
             ops.sgemm(bf["frames_mix"], LD, self.basis_fwd, LD, bf["dft_mix"], LD, B * Fr, LD, LD)
-            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, ns + 1, 64, self.spec_factor, self.spec_abs_exponent,
+            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, ns + 1, bf["x_planes"].shape[-1], self.spec_factor,
+                          self.spec_abs_exponent,
                           bf["x_pyr"], bf["x_planes"])
             self._mix_cache = mix_key if self._mix_cache_on else None
         return self._evaluate(xt, time, bf)
@@ -179,7 +180,8 @@ class ScoreModelNCSNpp(torch.nn.Module):
         Fr, Wp = bf["Fr"], bf["Wp"]
         ops.stft_frames(xt, self.window, B, ns, T, Fr, bf["frames"])
         ops.sgemm(bf["frames"], LD, self.basis_fwd, LD, bf["dft"], LD, B * ns * Fr, LD, LD)
-        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, 64, self.spec_factor, self.spec_abs_exponent,
+        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, bf["x_planes"].shape[-1], self.spec_factor,
+                      self.spec_abs_exponent,
                       bf["x_pyr"], bf["x_planes"])
         pyr = self.backbone(bf["x_planes"], bf["x_pyr"], time)
         ops.out_head(pyr, B, Wp, self.ch_in, ns, Fr, time, self.backbone.out_w, self.backbone.out_b,

@@ -39,6 +39,8 @@ const char* dsep_last_error(void);
 int dsep_abi_version(void);
 /* 1 if the running device is sm_100 (B200); the product path refuses anything else. */
 int dsep_device_ok(void);
+/* channel granularity of dsep_conv2d_tc's operands (Cin, Cin2 must be multiples of it): 32 */
+int dsep_conv_kblock(void);
 
 /* ---- tensor-core convolution -------------------------------------------------------------
  * out[b,h,w,n] = scale * ( acc_scale * ( sum_{tap,c} A[b,h+dy,w+dx,c] * Wt[tap,n,c]
@@ -46,7 +48,7 @@ int dsep_device_ok(void);
  *                          + bias[n] + film[b,n] + residual[b,h,w,n] )
  * stats[b,n,0..1] += (sum, sum of squares) of out[b,:,:,n]                       (if stats != NULL)
  * Implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators).  ksize 3 (pad 1) or 1.  A is a split
- * tensor [B,H,W,Cin] (Cin % 64 == 0); Wt a split tensor [ksize*ksize, Cout_pad, Cin] with
+ * tensor [B,H,W,Cin] (Cin % dsep_conv_kblock() == 0); Wt a split tensor [ksize*ksize, Cout_pad, Cin] with
  * Cout_pad in {16} or a multiple of 64; only the first cout_store channels are written, with
  * row pitch cout_store.  A2 [B,H,W,Cin2] / W2 [Cout_pad, Cin2] (Cin2 = 0: none) is a fused 1x1
  * convolution accumulated into the same tile (the ResBlock shortcut Conv_2).

@@ -107,9 +107,10 @@ def test_backbone_layerwise_vs_oracle(nf):
     with torch.no_grad():
         nr.ncsnpp_forward(params, x, t, taps=taps)
     xin = (2 * x - 1).permute(0, 2, 3, 1).contiguous().to(DEV)
-    xa = torch.zeros(B, 256, W, 64, device=DEV)
+    cpad = sm.backbone.conv_in.cin_pad
+    xa = torch.zeros(B, 256, W, cpad, device=DEV)
     xa[..., :6] = xin
-    planes = ops.Split.empty((B, 256, W, 64), DEV)
+    planes = ops.Split.empty((B, 256, W, cpad), DEV)
     ops.split_f16(xa, planes)
     pyr = sm.backbone(planes, xin, t.to(DEV))
     torch.cuda.synchronize()
@@ -127,6 +128,31 @@ def test_score_model_nf128_matches_reference_golden(golden):
     torch.cuda.synchronize()
     assert y.shape == (1, 2, 7680)
     assert rel_l2(y.cpu(), g["y"]) < 1e-4
+
+
+def test_score_model_nf32_matches_reference_golden(golden):
+    """nf=32 (channel counts 32/64/96: partial output tiles, 4-channel groups) vs the real reference."""
+    from diffsep_b200.backbone import cin_align
+    if cin_align() > 32:
+        pytest.skip("needs the 32-channel K-block build (DSEP_CONV_BK=32)")
+    g = golden("score_nf32.npz")
+    sm = _score_model(32)
+    xt, t, mix = cases.score_inputs(2, 2048, seed=7)
+    y = sm(xt.to(DEV), t.to(DEV), mix.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu(), g["y"]) < 1e-4
+
+
+def test_score_model_non_power_of_two_width_vs_oracle():
+    """T = 24000 -> 190 frames -> W = 192: level widths 192 ... 3 (odd), edge tiles everywhere."""
+    from oracle import score_ref as sr, weights as ow
+    params = ow.make_backbone_params(nf=64, seed=0)
+    xt, t, mix = cases.score_inputs(1, 24000, seed=11)
+    with torch.no_grad():
+        want = sr.score_forward(params, xt, t, mix)
+    y = _score_model(64)(xt.to(DEV), t.to(DEV), mix.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(y.cpu(), want) < 1e-4
 
 
 def test_score_model_tf32_grade_mode():
