@@ -86,7 +86,42 @@ __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
     return kBK == 64 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
 }
 
+// ---- "halo" mode (3x3, maps of at least 16 x 8): the A operand of all nine taps comes from ONE
+// shared-memory patch.  The output tile is 8 (w) x 16 (h) pixels; its 10 x 18 input patch of 64
+// channels is a single TMA box (out-of-image pixels zero-filled).  Patch row = y_p * 10 + x_p, so the
+// 128 operand rows of tap (dy, dx) are 16 groups of 8 consecutive patch rows starting at row
+// dy * 10 + dx, 10 rows (1280 B) apart: exactly a K-major UMMA descriptor with SBO = 1280 and a
+// shifted start address (the 128-byte swizzle is a function of the shared-memory address, which TMA
+// and tcgen05.mma share).  Shared-memory ingest per tile drops from 1152 KB to 668 KB, which is what
+// bounded the per-tap kernel (TMA-only time 1.0 ms vs MMA-only 1.2 ms on the level-0 conv).
+constexpr int kPatchW = 10, kPatchH = 18;
+constexpr int kPatchBytes = kPatchW * kPatchH * 128;          // 23040: one plane of a patch
+constexpr int kPatchPlane = 23 * 1024;                         // its 1024-aligned slot
+constexpr int kHaloAStages = 2;
+
 template <int NT>
+struct HaloCfg {
+    static constexpr int kBBytes = NT * 128;                   // one weight plane of a stage (64 ch)
+    static constexpr int kAStage = 2 * kPatchPlane;
+    static constexpr int kBStage = 2 * kBBytes;
+    static constexpr int kStagingBytes = kEpiWarps * 32 * 32 * 4;
+    static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes - kHaloAStages * kAStage;
+    static constexpr int kBStagesMax = kAvail / kBStage;
+    static constexpr int kBStages = kBStagesMax > 8 ? 8 : kBStagesMax;
+    static constexpr int kSmemBytes = kHaloAStages * kAStage + kBStages * kBStage + kStagingBytes + 512 + 1024;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes, bool base_off) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= 1ull << 46;
+    if (base_off) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;   // swizzle phase of the start row
+    d |= 2ull << 61;
+    return d;
+}
+
+template <int NT, bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -94,17 +129,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                const ConvParams p) {
     using Cfg = ConvCfg<NT>;
-    constexpr int NS = Cfg::kStages;
+    using HCfg = HaloCfg<NT>;
+    // per-tap mode: one ring of NS stages {A_hi, A_lo, W_hi, W_lo}; halo mode: a ring of NA patches
+    // {A_hi, A_lo} (barriers afull/aempty) and a ring of NS weight stages {W_hi, W_lo} (full/empty)
+    constexpr int NS = HALO ? HCfg::kBStages : Cfg::kStages;
+    constexpr int NA = kHaloAStages;
+    constexpr int kRingBytes = HALO ? NA * HCfg::kAStage + NS * HCfg::kBStage : NS * Cfg::kStageBytes;
+    constexpr int kStagingBytes = HALO ? HCfg::kStagingBytes : Cfg::kStagingBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    float* staging = reinterpret_cast<float*>(smem + NS * Cfg::kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes + Cfg::kStagingBytes);
+    float* staging = reinterpret_cast<float*>(smem + kRingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes + kStagingBytes);
     uint64_t* full = bars;             // [NS]   TMA -> MMA
     uint64_t* empty = bars + NS;       // [NS]   MMA -> TMA
     uint64_t* tfull = bars + 2 * NS;   // [2]    MMA -> epilogue
     uint64_t* tempty = tfull + 2;      // [2]    epilogue -> MMA
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* afull = tempty + 2;      // [NA]   halo patches: TMA -> MMA
+    uint64_t* aempty = afull + NA;     // [NA]   MMA -> TMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty + NA);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -129,6 +172,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], NT >= 64 ? kEpiWarps : 4);   // narrow tiles: only 4 warps drain TMEM
         }
+        for (int i = 0; i < NA; ++i) {
+            mbar_init(&afull[i], 1);
+            mbar_init(&aempty[i], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
@@ -142,8 +189,115 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int kiters = p.taps * p.kblocks + p.kblocks2;
     const uint32_t stage_tx = (three ? 2u : 1u) * static_cast<uint32_t>(kABytes + Cfg::kBBytes);
 
-    if (warp == 0 && lane == 0) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp == 0 && lane == 0 && HALO) {
+        // ------------------------------------------------------------------ TMA producer (halo mode)
+        if constexpr (HALO) {
+            const uint32_t planes = three ? 2u : 1u;
+            int bs = 0, as_ = 0;
+            uint32_t bph = 0, aph = 0;
+            auto load_weights = [&](const CUtensorMap* whi, const CUtensorMap* wlo, int kcol, int wrow) {
+                mbar_wait(&empty[bs], bph ^ 1u);
+                uint8_t* sb = stage_base + NA * HCfg::kAStage + bs * HCfg::kBStage;
+                if (p.debug & 2) {
+                    mbar_arrive(&full[bs]);
+                    if (++bs == NS) { bs = 0; bph ^= 1u; }
+                    return;
+                }
+                mbar_arrive_expect_tx(&full[bs], planes * HCfg::kBBytes);
+                const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);
+                const int boff = static_cast<int>(rank) * (HCfg::kBBytes / 2);
+                tma_load_2d_mc(sb + boff, whi, &full[bs], kcol, wrow_h, 0x3);
+                if (three) tma_load_2d_mc(sb + HCfg::kBBytes + boff, wlo, &full[bs], kcol, wrow_h, 0x3);
+                if (++bs == NS) { bs = 0; bph ^= 1u; }
+            };
+            for (int item = cluster_id; item < p.total_items; item += num_clusters) {
+                const int nt = item % p.tiles_n;
+                int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);
+                const int wt = r % p.tiles_w; r /= p.tiles_w;
+                const int ht = r % p.tiles_h; r /= p.tiles_h;
+                const int w0 = wt << 3, h0 = ht << 4, b0 = r;
+                const int n0 = nt * NT;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&aempty[as_], aph ^ 1u);
+                    uint8_t* sa = stage_base + as_ * HCfg::kAStage;
+                    if (p.debug & 2) {
+                        mbar_arrive(&afull[as_]);
+                    } else {
+                        mbar_arrive_expect_tx(&afull[as_], planes * kPatchBytes);
+                        tma_load_4d(sa, &tm_a_hi, &afull[as_], kb * 64, w0 - 1, h0 - 1, b0);
+                        if (three) tma_load_4d(sa + kPatchPlane, &tm_a_lo, &afull[as_], kb * 64, w0 - 1, h0 - 1, b0);
+                    }
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                    for (int tap = 0; tap < 9; ++tap) load_weights(&tm_w_hi, &tm_w_lo, kb * 64, tap * p.Cout_pad + n0);
+                }
+                for (int kb = 0; kb < p.kblocks2; ++kb) {       // fused 1x1 shortcut: the tile itself, no halo
+                    mbar_wait(&aempty[as_], aph ^ 1u);
+                    uint8_t* sa = stage_base + as_ * HCfg::kAStage;
+                    mbar_arrive_expect_tx(&afull[as_], planes * 16384u);
+                    tma_load_4d(sa, &tm_a2_hi, &afull[as_], kb * 64, w0, h0, b0);
+                    if (three) tma_load_4d(sa + kPatchPlane, &tm_a2_lo, &afull[as_], kb * 64, w0, h0, b0);
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                    load_weights(&tm_w2_hi, &tm_w2_lo, kb * 64, n0);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && HALO) {
+        // ------------------------------------------------------------------ MMA issuer (halo mode)
+        if constexpr (HALO) {
+            constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
+            constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
+            int bs = 0, as_ = 0;
+            uint32_t bph = 0, aph = 0;
+            int it = 0;
+            for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 2 * NT;
+                uint32_t accumulate = 0;
+                // one weight stage against the A rows starting at byte offset a_off, groups sbo bytes apart
+                auto issue = [&](uint32_t a_base, uint32_t a_off, uint32_t sbo) {
+                    mbar_wait(&full[bs], bph);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(stage_base + NA * HCfg::kAStage + bs * HCfg::kBStage);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (p.debug & 1) break;
+                        const uint64_t a_hi = umma_desc_sw128_sbo(a_base + a_off + k * 32, sbo, (p.debug & 8) != 0);
+                        const uint64_t b_hi = umma_desc_sw128(sb + k * 32);          // W_hi rows, then W_lo rows
+                        if (three) {
+                            umma_f16(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
+                            const uint64_t a_lo = umma_desc_sw128_sbo(a_base + kPatchPlane + a_off + k * 32, sbo, (p.debug & 8) != 0);
+                            umma_f16(d_tmem, a_lo, b_hi, idesc_n, 1);
+                        } else {
+                            umma_f16(d_tmem, a_hi, b_hi, idesc_n, accumulate);
+                        }
+                        accumulate = 1;
+                    }
+                    umma_commit_mc(&empty[bs], 0x3);
+                    if (++bs == NS) { bs = 0; bph ^= 1u; }
+                };
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&afull[as_], aph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + as_ * HCfg::kAStage);
+                    for (int tap = 0; tap < 9; ++tap)
+                        issue(sa, static_cast<uint32_t>(((tap / 3) * kPatchW + tap % 3) * 128), kPatchW * 128);
+                    umma_commit(&aempty[as_]);
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                }
+                for (int kb = 0; kb < p.kblocks2; ++kb) {
+                    mbar_wait(&afull[as_], aph);
+                    tc_fence_after();
+                    issue(smem_u32(stage_base + as_ * HCfg::kAStage), 0u, 1024u);
+                    umma_commit(&aempty[as_]);
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (per-tap mode)
         int stage = 0;
         uint32_t phase = 0;
         for (int item = cluster_id; item < p.total_items; item += num_clusters) {
@@ -475,21 +629,21 @@ struct ConvMaps {
     CUtensorMap a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, w2_hi, w2_lo;
 };
 
-template <int NT>
+template <int NT, bool HALO>
 static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
+    constexpr int kSmem = HALO ? HaloCfg<NT>::kSmemBytes : ConvCfg<NT>::kSmemBytes;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ConvCfg<NT>::kSmemBytes);
+        attr_err = cudaFuncSetAttribute(conv_tc_kernel<NT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     });
     if (attr_err != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_tc_kernel<%d>): %s", NT, cudaGetErrorString(attr_err));
+        set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>): %s", NT, (int)HALO, cudaGetErrorString(attr_err));
         return DSEP_ERR_CUDA;
     }
     const int max_clusters = num_sms() / 2;
     const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
-    conv_tc_kernel<NT><<<grid, kThreads, ConvCfg<NT>::kSmemBytes, stream>>>(
+    conv_tc_kernel<NT, HALO><<<grid, kThreads, kSmem, stream>>>(
         m.a_hi, m.a_lo, m.w_hi, m.w_lo, m.a2_hi, m.a2_lo, m.w2_hi, m.w2_lo, p);
     return check_launch("conv_tc_kernel");
 }
@@ -531,6 +685,10 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     p.taps = ksize * ksize;
     int tw = 1 << ilog2(W); if (tw > 16) tw = 16;
     int th = 1 << ilog2(H); if (th > 128 / tw) th = 128 / tw;
+    // halo mode: 3x3 over a map of at least 16 x 8 and wide output tiles; fixed 8 (w) x 16 (h) tile
+    static const int halo_env = getenv("DSEP_CONV_HALO") ? atoi(getenv("DSEP_CONV_HALO")) : 1;
+    const bool halo = halo_env != 0 && kBK == 64 && ksize == 3 && W >= 8 && H >= 16 && Cout_pad != 16;
+    if (halo) { tw = 8; th = 16; }
     const int tb = 128 / (tw * th);
     DSEP_REQUIRE(stats == nullptr || (Cout_pad != 16 && tb == 1),
                  "conv2d_tc: fused statistics need Cout >= 64 and 128-pixel tiles inside one batch entry "
@@ -554,7 +712,8 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     {
         const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+        const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)(halo ? kPatchW : tw),
+                                    (cuuint32_t)(halo ? kPatchH : th), (cuuint32_t)tb};
         const cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)p.taps * Cout_pad};
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
         const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
@@ -588,9 +747,10 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
         m.a2_hi = m.a_hi; m.a2_lo = m.a_lo; m.w2_hi = m.w_hi; m.w2_lo = m.w_lo;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (halo) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);
     switch (NT) {
-        case 16: return launch_conv<16>(m, p, s);
-        case 64: return launch_conv<64>(m, p, s);
-        default: return launch_conv<128>(m, p, s);
+        case 16: return launch_conv<16, false>(m, p, s);
+        case 64: return launch_conv<64, false>(m, p, s);
+        default: return launch_conv<128, false>(m, p, s);
     }
 }
