@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libdsep.so"
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -23,11 +23,23 @@ class SdeParams(C.Structure):
                 ("T_end", C.c_float)]
 
 
+class ConvArgs(C.Structure):
+    """dsep_conv_args of include/dsep.h (field order and types must match exactly)."""
+    _fields_ = [("a_hi", _p), ("a_lo", _p), ("x0", _p), ("x1", _p), ("C0", _i), ("C1", _i), ("sc", _p), ("sh", _p),
+                ("act", _i), ("B", _i), ("H", _i), ("W", _i), ("Cin", _i), ("w_hi", _p), ("w_lo", _p),
+                ("Cout_pad", _i), ("ksize", _i), ("a2_hi", _p), ("a2_lo", _p), ("s0", _p), ("s1", _p), ("S0", _i),
+                ("S1", _i), ("Cin2", _i), ("w2_hi", _p), ("w2_lo", _p), ("bias", _p), ("film", _p),
+                ("film_stride", _i), ("residual", _p), ("scale", _f), ("acc_scale", _f), ("out", _p),
+                ("cout_store", _i), ("stats", _p), ("passes", _i)]
+
+
 # name -> argument types, exactly the prototypes of include/dsep.h (return type int)
 PROTOTYPES = {
     "dsep_conv2d_tc": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _p, _p, _p, _i, _p, _f, _f, _p, _i,
                        _p, _i, _p],
     "dsep_split_f16": [_p, _i64, _f, _p, _p, _p],
+    "dsep_conv2d_fused": [C.POINTER(ConvArgs), _p],
+    "dsep_gn_tables": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p],
     "dsep_channel_stats": [_p, _i, _i, _i, _p, _p],
     "dsep_zero": [_p, _i64, _p],
     "dsep_gn_act_split": [_p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p, _p],

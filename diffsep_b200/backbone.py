@@ -19,6 +19,7 @@ B200-first design, not a module tree:
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -150,10 +151,12 @@ class Arena:
 class NCSNppB200:
     """The NCSN++ backbone: ``__call__(x_planes, x_pyramid, t) -> pyramid`` over a replayed plan."""
 
-    def __init__(self, params, nf=128, ch_in=6, ch_out=4, device="cuda", passes=3):
+    def __init__(self, params, nf=128, ch_in=6, ch_out=4, device="cuda", passes=3, fuse=None):
         ops.require_device()
         self.device = torch.device(device)
         self.nf, self.ch_in, self.ch_out, self.passes = nf, ch_in, ch_out, passes
+        # in-kernel GroupNorm/SiLU/concat prologue (dsep_conv2d_fused) where shapes allow
+        self.fuse = bool(int(os.environ.get("DSEP_FUSE", "1"))) if fuse is None else bool(fuse)
         self.temb_dim = 4 * nf
         self._plans = {}
         self._load(params)
@@ -335,8 +338,40 @@ class _Plan:
             bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
             acc_scale=cw.acc_scale, passes=net.passes, a2=a2, Cin2=cin2, w2=w2, stats=stats))
 
+    def _fusable(self, H, W, *channels):
+        """dsep_conv2d_fused's in-kernel prologue: map of at least 16 x 8, 64-channel granularity"""
+        return (self.net.fuse and cin_align() == 64 and H >= 16 and W >= 8
+                and all(c % 64 == 0 for c in channels if c))
+
+    def _tables(self, st0, C0, st1, C1, P, gamma, beta):
+        """GroupNorm scale/shift tables [B, C0+C1] for the fused prologue (tiny kernel)."""
+        ar, B = self.arena, self.B
+        sc, sh = ar.f32(B, C0 + C1), ar.f32(B, C0 + C1)
+        g = gn_groups(C0 + C1)
+        self.steps.append(lambda: ops.gn_tables(st0, C0, st1, C1, B, P, g, gamma, beta, GN_EPS, sc, sh))
+        return sc, sh
+
+    def _conv_fused(self, H, W, cin, cw: ConvWeight, out, cout_store, x0, C0, x1, C1, sc, sh, act, film=None,
+                    residual=None, scale=1.0, shortcut_raw=None, stats=None):
+        net, B = self.net, self.B
+        film_v, stride = None, 0
+        if film is not None:
+            film_v, stride = self.film[:, film:], self.film.shape[1]
+        kw = {}
+        if shortcut_raw is not None:
+            s0, S0, s1, S1 = shortcut_raw
+            kw = dict(s0=s0, S0=S0, s1=s1, S1=S1, Cin2=cw.cin2_pad, w2=cw.planes2)
+        self.steps.append(lambda: ops.conv2d_fused(
+            B, H, W, cin, cw.planes, cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1, sc=sc,
+            sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
+            acc_scale=cw.acc_scale, stats=stats, passes=net.passes, **kw))
+
     def _resblock(self, rb, x: Act, skip: Act = None, mode=0, want_stats=True) -> Act:
-        """ResnetBlockBigGANpp (layerspp.py:291-323).  mode 0 plain, 1 up, 2 down."""
+        """ResnetBlockBigGANpp (layerspp.py:291-323).  mode 0 plain, 1 up, 2 down.
+
+        On maps of at least 16 x 8 a plain block is TWO launches (+ two tiny table kernels): both
+        GroupNorm+SiLU prologues, the channel concat and the 1x1 shortcut run inside the conv kernels.
+        Up/down blocks keep one FIR pass in front (it also applies GN0+SiLU)."""
         ar, B = self.arena, self.B
         C0, C1 = x.C, (skip.C if skip is not None else 0)
         Cin, Cout, H, W = C0 + C1, rb["cout"], x.H, x.W
@@ -346,9 +381,52 @@ class _Plan:
         st1 = self._ensure_stats(skip) if skip is not None else None
         x0, x1 = x.t, (skip.t if skip is not None else None)
         Ho, Wo = (H * 2, W * 2) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
-        a = ar.split(B, Ho, Wo, Cin)
-        r = ar.split(B, Ho, Wo, Cin) if rb["has_shortcut"] else None
         gam0, bet0 = rb["gn0"]
+        gam1, bet1 = rb["gn1"]
+        fused = self._fusable(Ho, Wo, C0, C1, Cout)
+        h = Act(ar.f32(B, Ho, Wo, Cout), Cout, Ho, Wo, self._fused_slot(Ho, Wo, Cout))
+        out_slot = self._fused_slot(Ho, Wo, Cout) if want_stats else None
+
+        if fused and mode == 0:
+            sc0, sh0 = self._tables(st0, C0, st1, C1, H * W, gam0, bet0)
+            self._conv_fused(H, W, Cin, rb["conv0"], h.t, Cout, x0, C0, x1, C1, sc0, sh0, 1, film=rb["film_off"],
+                             stats=h.st)
+            ar.release(sc0); ar.release(sh0)
+            st_h = self._ensure_stats(h)
+            sc1, sh1 = self._tables(st_h, Cout, None, 0, H * W, gam1, bet1)
+            out = Act(ar.f32(B, H, W, Cout), Cout, H, W, out_slot)
+            if rb["has_shortcut"]:
+                self._conv_fused(H, W, Cout, rb["conv1"], out.t, Cout, h.t, Cout, None, 0, sc1, sh1, 1,
+                                 scale=INV_SQRT2, shortcut_raw=(x0, C0, x1, C1), stats=out.st)
+            else:
+                assert x1 is None and Cin == Cout
+                self._conv_fused(H, W, Cout, rb["conv1"], out.t, Cout, h.t, Cout, None, 0, sc1, sh1, 1,
+                                 residual=x0, scale=INV_SQRT2, stats=out.st)
+            ar.release(sc1); ar.release(sh1)
+            ar.release(h.t)
+            return out
+
+        a = ar.split(B, Ho, Wo, Cin)
+        if fused:
+            # up / down block on a large map: one FIR pass writes a = FIR(SiLU(GN0(x))) as planes for
+            # Conv_0 and FIR(x) in fp32; Conv_1 applies GN1+SiLU to h and splits FIR(x) for the
+            # shortcut in-kernel (all of a launch's A patches come from ONE agent: TMA or workers)
+            assert mode != 0 and x1 is None and rb["has_shortcut"]
+            xr = ar.f32(B, Ho, Wo, Cin)
+            self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
+                                                       a=a, y=xr))
+            self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st)
+            ar.release(a)
+            st_h = self._ensure_stats(h)
+            sc1, sh1 = self._tables(st_h, Cout, None, 0, Ho * Wo, gam1, bet1)
+            out = Act(ar.f32(B, Ho, Wo, Cout), Cout, Ho, Wo, out_slot)
+            self._conv_fused(Ho, Wo, Cout, rb["conv1"], out.t, Cout, h.t, Cout, None, 0, sc1, sh1, 1,
+                             scale=INV_SQRT2, shortcut_raw=(xr, Cin, None, 0), stats=out.st)
+            ar.release(sc1); ar.release(sh1)
+            ar.release(xr)
+            ar.release(h.t)
+            return out
+        r = ar.split(B, Ho, Wo, Cin) if rb["has_shortcut"] else None
         if mode == 0:
             self.steps.append(lambda: ops.gn_act_split(x0, C0, st0, x1, C1, st1, B, H * W, g0, gam0, bet0, GN_EPS,
                                                        1, a=a, r=r))
@@ -356,18 +434,16 @@ class _Plan:
             assert x1 is None and r is not None
             self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
                                                        a=a, r=r))
-        h = Act(ar.f32(B, Ho, Wo, Cout), Cout, Ho, Wo, self._fused_slot(Ho, Wo, Cout))
         self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st)
         ar.release(a)
         g1 = gn_groups(Cout)
         st_h = self._ensure_stats(h)
         a2 = ar.split(B, Ho, Wo, Cout)
-        gam1, bet1 = rb["gn1"]
         ht = h.t
         self.steps.append(lambda: ops.gn_act_split(ht, Cout, st_h, None, 0, None, B, Ho * Wo, g1, gam1, bet1,
                                                    GN_EPS, 1, a=a2))
         # conv1 never reads h (only a2), so its buffer is reused for the block output
-        out = Act(h.t, Cout, Ho, Wo, self._fused_slot(Ho, Wo, Cout) if want_stats else None)
+        out = Act(h.t, Cout, Ho, Wo, out_slot)
         if rb["has_shortcut"]:
             self._conv(a2, Ho, Wo, Cout, rb["conv1"], out.t, Cout, scale=INV_SQRT2, a2=r, stats=out.st)
             ar.release(r)
@@ -383,13 +459,19 @@ class _Plan:
         S = H * W
         g = gn_groups(Cc)
         st = self._ensure_stats(x)
-        a = ar.split(B, H, W, Cc)
         gam, bet = at["gn"]
         xt = x.t
-        self.steps.append(lambda: ops.gn_act_split(xt, Cc, st, None, 0, None, B, S, g, gam, bet, GN_EPS, 0, a=a))
         qkv = ar.f32(B, S, 3 * Cc)
-        self._conv(a, H, W, Cc, at["qkv"], qkv, 3 * Cc)
-        o = a   # the GN'd input planes are dead once q, k, v exist
+        o = ar.split(B, H, W, Cc)
+        if self._fusable(H, W, Cc):     # GroupNorm (no activation) inside the stacked q/k/v projection
+            sc, sh = self._tables(st, Cc, None, 0, S, gam, bet)
+            self._conv_fused(H, W, Cc, at["qkv"], qkv, 3 * Cc, xt, Cc, None, 0, sc, sh, 0)
+            ar.release(sc); ar.release(sh)
+        else:
+            a = ar.split(B, H, W, Cc)
+            self.steps.append(lambda: ops.gn_act_split(xt, Cc, st, None, 0, None, B, S, g, gam, bet, GN_EPS, 0, a=a))
+            self._conv(a, H, W, Cc, at["qkv"], qkv, 3 * Cc)
+            ar.release(a)
         self.steps.append(lambda: ops.attention(qkv, B, S, Cc, float(Cc) ** -0.5, o))
         out = Act(ar.f32(B, H, W, Cc), Cc, H, W, self._fused_slot(H, W, Cc))
         self._conv(o, H, W, Cc, at["proj"], out.t, Cc, residual=xt, scale=INV_SQRT2, stats=out.st)

@@ -55,6 +55,12 @@ struct ConvParams {
     float scale, acc_scale;
     float* out;
     double* stats;         // [B, cout_store, 2] or null
+    // fused prologue (halo mode): the A patch is built in-kernel from fp32 activations instead of
+    // arriving as split planes by TMA.  main operand: act(x * sc + sh) of the channel-concatenated
+    // [fx0 (fC0 ch) | fx1 (fC1 ch)]; shortcut operand: the raw [gx0 | gx1] (identity).
+    const float* fx0; const float* fx1; int fC0, fC1;
+    const float* fsc; const float* fsh; int fact;
+    const float* gx0; const float* gx1; int gC0, gC1;
     int debug;             // DSEP_CONV_DEBUG bitmask: 1 skip MMA issue, 2 skip TMA loads, 4 skip epilogue stores (timing experiments)
 };
 
@@ -119,6 +125,81 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
     if (base_off) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;   // swizzle phase of the start row
     d |= 2ull << 61;
     return d;
+}
+
+// Builds one 64-channel A patch (PH x PW pixels, row = py * PW + px, 128-byte-swizzled K-major rows of
+// (hi, lo) fp16) from fp32 activations: y = act(x * sc[c] + sh[c]), zero outside the image (the conv
+// pads the ACTIVATED tensor).  Called by the 256 worker threads; wtid = 0..255.  Replaces the
+// GroupNorm-apply + SiLU + split pass (and the channel concat) that used to run as its own kernel.
+template <int PW, int PH>
+__device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bool want_lo, const float* x0, int C0,
+                                            const float* x1, int C1, int kb, const float* sc, const float* sh,
+                                            int act, int b, int h_org, int w_org, int B, int H, int W, int wtid) {
+    constexpr int kItems = PW * PH * 8;                    // (row, 8-channel chunk) pairs
+    constexpr int kIter = (kItems + 255) / 256;
+    const int j = wtid & 7;
+    const int c = kb * 64 + j * 8;                          // first of this thread's 8 channels (concatenated)
+    const float* src;
+    int cs, cl;
+    if (c < C0) { src = x0; cs = C0; cl = c; } else { src = x1; cs = C1; cl = c - C0; }
+    float k_sc[8], k_sh[8];
+    if (sc != nullptr) {
+        const int Ct = C0 + C1;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + static_cast<size_t>(b < B ? b : 0) * Ct + c));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(sc + static_cast<size_t>(b < B ? b : 0) * Ct + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(sh + static_cast<size_t>(b < B ? b : 0) * Ct + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(sh + static_cast<size_t>(b < B ? b : 0) * Ct + c + 4));
+        k_sc[0] = a0.x; k_sc[1] = a0.y; k_sc[2] = a0.z; k_sc[3] = a0.w;
+        k_sc[4] = a1.x; k_sc[5] = a1.y; k_sc[6] = a1.z; k_sc[7] = a1.w;
+        k_sh[0] = b0.x; k_sh[1] = b0.y; k_sh[2] = b0.z; k_sh[3] = b0.w;
+        k_sh[4] = b1.x; k_sh[5] = b1.y; k_sh[6] = b1.z; k_sh[7] = b1.w;
+    }
+    float4 v[kIter][2];
+    bool inb[kIter];
+#pragma unroll
+    for (int u = 0; u < kIter; ++u) {                        // all loads first: ~12 x 16 B in flight per thread
+        const int item = wtid + u * 256;
+        const int r = item >> 3;
+        const int py = r / PW, px = r - py * PW;
+        const int h = h_org + py, w = w_org + px;
+        inb[u] = item < kItems && b < B && h >= 0 && h < H && w >= 0 && w < W;
+        if (inb[u]) {
+            const float* q = src + ((static_cast<size_t>(b) * H + h) * W + w) * cs + cl;
+            v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
+            v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
+        } else {
+            v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kIter; ++u) {
+        const int item = wtid + u * 256;
+        if (item >= kItems) break;
+        const int r = item >> 3;
+        float y[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+        if (inb[u] && sc != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = fmaf(y[e], k_sc[e], k_sh[e]);
+                if (act) t = __fdividef(t, 1.0f + __expf(-t));
+                y[e] = t;
+            }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = fminf(fmaxf(y[2 * e], -60000.0f), 60000.0f);
+            const float bq = fminf(fmaxf(y[2 * e + 1], -60000.0f), 60000.0f);
+            const __half2 h2 = __floats2half2_rn(a, bq);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(a - back.x, bq - back.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (want_lo) *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
 }
 
 template <int NT, bool HALO>
@@ -217,27 +298,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const int ht = r % p.tiles_h; r /= p.tiles_h;
                 const int w0 = wt << 3, h0 = ht << 4, b0 = r;
                 const int n0 = nt * NT;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int hal = p.taps == 9 ? 1 : 0;
+                const uint32_t patch_bytes = p.taps == 9 ? kPatchBytes : 16384u;
+                // patch order per tile: shortcut K-blocks first (one tap each), then the main ones, so
+                // that the slot the NEXT tile's first patch needs is released half-way through this
+                // tile's MMAs.  Every agent waits for every slot in ring order (even those it does not
+                // fill): an mbarrier parity wait must never fall a whole phase behind.
+                for (int kb = 0; kb < p.kblocks2; ++kb) {
                     mbar_wait(&aempty[as_], aph ^ 1u);
-                    uint8_t* sa = stage_base + as_ * HCfg::kAStage;
-                    if (p.debug & 2) {
-                        mbar_arrive(&afull[as_]);
-                    } else {
-                        mbar_arrive_expect_tx(&afull[as_], planes * kPatchBytes);
-                        tma_load_4d(sa, &tm_a_hi, &afull[as_], kb * 64, w0 - 1, h0 - 1, b0);
-                        if (three) tma_load_4d(sa + kPatchPlane, &tm_a_lo, &afull[as_], kb * 64, w0 - 1, h0 - 1, b0);
+                    if (p.gx0 == nullptr) {       // split planes by TMA (otherwise the worker warps build it)
+                        uint8_t* sa = stage_base + as_ * HCfg::kAStage;
+                        if (p.debug & 2) {
+                            mbar_arrive(&afull[as_]);
+                        } else {
+                            mbar_arrive_expect_tx(&afull[as_], planes * 16384u);
+                            tma_load_4d(sa, &tm_a2_hi, &afull[as_], kb * 64, w0, h0, b0);
+                            if (three) tma_load_4d(sa + kPatchPlane, &tm_a2_lo, &afull[as_], kb * 64, w0, h0, b0);
+                        }
                     }
                     if (++as_ == NA) { as_ = 0; aph ^= 1u; }
-                    for (int tap = 0; tap < 9; ++tap) load_weights(&tm_w_hi, &tm_w_lo, kb * 64, tap * p.Cout_pad + n0);
-                }
-                for (int kb = 0; kb < p.kblocks2; ++kb) {       // fused 1x1 shortcut: the tile itself, no halo
-                    mbar_wait(&aempty[as_], aph ^ 1u);
-                    uint8_t* sa = stage_base + as_ * HCfg::kAStage;
-                    mbar_arrive_expect_tx(&afull[as_], planes * 16384u);
-                    tma_load_4d(sa, &tm_a2_hi, &afull[as_], kb * 64, w0, h0, b0);
-                    if (three) tma_load_4d(sa + kPatchPlane, &tm_a2_lo, &afull[as_], kb * 64, w0, h0, b0);
-                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
                     load_weights(&tm_w2_hi, &tm_w2_lo, kb * 64, n0);
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&aempty[as_], aph ^ 1u);
+                    if (p.fx0 == nullptr) {
+                        uint8_t* sa = stage_base + as_ * HCfg::kAStage;
+                        if (p.debug & 2) {
+                            mbar_arrive(&afull[as_]);
+                        } else {
+                            mbar_arrive_expect_tx(&afull[as_], planes * patch_bytes);
+                            tma_load_4d(sa, &tm_a_hi, &afull[as_], kb * 64, w0 - hal, h0 - hal, b0);
+                            if (three)
+                                tma_load_4d(sa + kPatchPlane, &tm_a_lo, &afull[as_], kb * 64, w0 - hal, h0 - hal, b0);
+                        }
+                    }
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                    for (int tap = 0; tap < p.taps; ++tap)
+                        load_weights(&tm_w_hi, &tm_w_lo, kb * 64, tap * p.Cout_pad + n0);
                 }
             }
         }
@@ -277,19 +374,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     umma_commit_mc(&empty[bs], 0x3);
                     if (++bs == NS) { bs = 0; bph ^= 1u; }
                 };
+                for (int kb = 0; kb < p.kblocks2; ++kb) {      // fused 1x1 shortcut K-blocks
+                    mbar_wait(&afull[as_], aph);
+                    tc_fence_after();
+                    issue(smem_u32(stage_base + as_ * HCfg::kAStage), 0u, 1024u);
+                    umma_commit(&aempty[as_]);
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&afull[as_], aph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stage_base + as_ * HCfg::kAStage);
-                    for (int tap = 0; tap < 9; ++tap)
-                        issue(sa, static_cast<uint32_t>(((tap / 3) * kPatchW + tap % 3) * 128), kPatchW * 128);
-                    umma_commit(&aempty[as_]);
-                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
-                }
-                for (int kb = 0; kb < p.kblocks2; ++kb) {
-                    mbar_wait(&afull[as_], aph);
-                    tc_fence_after();
-                    issue(smem_u32(stage_base + as_ * HCfg::kAStage), 0u, 1024u);
+                    if (p.taps == 9) {
+                        for (int tap = 0; tap < 9; ++tap)
+                            issue(sa, static_cast<uint32_t>(((tap / 3) * kPatchW + tap % 3) * 128), kPatchW * 128);
+                    } else {
+                        issue(sa, 0u, 1024u);
+                    }
                     umma_commit(&aempty[as_]);
                     if (++as_ == NA) { as_ = 0; aph ^= 1u; }
                 }
@@ -401,8 +502,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 }
             }
         };
-        int it = 0;
-        for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
+        auto do_epilogue = [&](int item, int it) {
             const int as = it & 1;
             const int nt = item % p.tiles_n;
             int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);      // this CTA's M tile of the pair
@@ -566,6 +666,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     }
                 }
             }
+        };
+
+        bool worker_builds = false;
+        if constexpr (HALO) worker_builds = p.fx0 != nullptr || p.gx0 != nullptr;
+        if (!worker_builds) {
+            int it = 0;
+            for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) do_epilogue(item, it);
+        } else {
+            if constexpr (HALO) {
+                // Worker schedule per tile i: build the patches of tile i that are theirs (in ring order:
+                // shortcut K-blocks, then main), then run the epilogue of tile i-1 while the tensor core
+                // chews on the main patches.  Patches live in the 2-slot A ring shared with the TMA
+                // producer (which fills those that still arrive as planes); the epilogue of tile i-1
+                // only has to finish before the MMAs of tile i+1 (double-buffered TMEM).
+                const int wtid = threadIdx.x - 128;
+                int as_ = 0;
+                uint32_t aph = 0;
+                int it = 0, prev_item = -1;
+                for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
+                    int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);
+                    const int wt = r % p.tiles_w; r /= p.tiles_w;
+                    const int ht = r % p.tiles_h; r /= p.tiles_h;
+                    const int w0 = wt << 3, h0 = ht << 4, b0 = r;
+                    const int total = p.kblocks + p.kblocks2;
+                    for (int pi = 0; pi < total; ++pi) {
+                        const bool second = pi < p.kblocks2;
+                        const bool mine = second ? p.gx0 != nullptr : p.fx0 != nullptr;
+                        mbar_wait(&aempty[as_], aph ^ 1u);      // stay phase-locked even on patches TMA fills
+                        if (mine) {
+                            uint8_t* sa = stage_base + as_ * HCfg::kAStage;
+                            if (!(p.debug & 2)) {
+                                if (second)
+                                    build_patch<8, 16>(sa, sa + kPatchPlane, three, p.gx0, p.gC0, p.gx1, p.gC1, pi,
+                                                       nullptr, nullptr, 0, b0, h0, w0, p.B, p.H, p.W, wtid);
+                                else if (p.taps == 9)
+                                    build_patch<kPatchW, kPatchH>(sa, sa + kPatchPlane, three, p.fx0, p.fC0, p.fx1, p.fC1,
+                                                                  pi - p.kblocks2, p.fsc, p.fsh, p.fact, b0, h0 - 1,
+                                                                  w0 - 1, p.B, p.H, p.W, wtid);
+                                else
+                                    build_patch<8, 16>(sa, sa + kPatchPlane, three, p.fx0, p.fC0, p.fx1, p.fC1,
+                                                       pi - p.kblocks2, p.fsc, p.fsh, p.fact, b0, h0, w0, p.B, p.H, p.W,
+                                                       wtid);
+                            }
+                            // generic-proxy writes -> visible to the tensor core's async proxy, then publish
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            asm volatile("bar.sync 1, 256;" ::: "memory");
+                            if (wtid == 0) mbar_arrive(&afull[as_]);
+                        }
+                        if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                    }
+                    if (prev_item >= 0) do_epilogue(prev_item, it - 1);
+                    prev_item = item;
+                }
+                if (prev_item >= 0) do_epilogue(prev_item, it - 1);
+            }
         }
         flush_stats();
     }
@@ -658,16 +813,15 @@ static int ilog2(int v) {
 
 extern "C" int dsep_conv_kblock(void) { return dsep::kBK; }
 
-extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
-                              const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
-                              const void* a2_hi, const void* a2_lo, int Cin2, const void* w2_hi,
-                              const void* w2_lo, const float* bias, const float* film, int film_stride,
-                              const float* residual, float scale, float acc_scale, float* out,
-                              int cout_store, double* stats, int passes, dsep_stream_t stream) {
+extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) {
     using namespace dsep;
-    DSEP_REQUIRE(a_hi && w_hi && out, "conv2d_tc: null operand");
+    DSEP_REQUIRE(g != nullptr, "conv2d: null argument block");
+    const int B = g->B, H = g->H, W = g->W, Cin = g->Cin, Cout_pad = g->Cout_pad, ksize = g->ksize;
+    const int Cin2 = g->Cin2, cout_store = g->cout_store, passes = g->passes;
+    const bool main_fused = g->x0 != nullptr, short_fused = g->s0 != nullptr;
+    DSEP_REQUIRE((g->a_hi || main_fused) && g->w_hi && g->out, "conv2d_tc: null operand");
     DSEP_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3 (got %d)", passes);
-    DSEP_REQUIRE(passes == 1 || (a_lo && w_lo), "conv2d_tc: passes=3 needs the lo planes");
+    DSEP_REQUIRE(passes == 1 || ((g->a_lo || main_fused) && g->w_lo), "conv2d_tc: passes=3 needs the lo planes");
     DSEP_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize must be 1 or 3 (got %d)", ksize);
     DSEP_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_tc: empty tensor");
     DSEP_REQUIRE(Cin > 0 && Cin % kBK == 0, "conv2d_tc: Cin must be a multiple of %d (got %d)", kBK, Cin);
@@ -676,7 +830,8 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     DSEP_REQUIRE(cout_store > 0 && cout_store <= Cout_pad, "conv2d_tc: bad cout_store %d", cout_store);
     DSEP_REQUIRE(Cout_pad == 16 || cout_store % 4 == 0, "conv2d_tc: cout_store must be a multiple of 4");
     DSEP_REQUIRE(Cin2 >= 0 && Cin2 % kBK == 0, "conv2d_tc: Cin2 must be a multiple of %d (got %d)", kBK, Cin2);
-    DSEP_REQUIRE(Cin2 == 0 || (a2_hi && w2_hi && (passes == 1 || (a2_lo && w2_lo))),
+    DSEP_REQUIRE(Cin2 == 0 || ((g->a2_hi || short_fused) && g->w2_hi &&
+                               (passes == 1 || ((g->a2_lo || short_fused) && g->w2_lo))),
                  "conv2d_tc: fused 1x1 operand (Cin2=%d) needs its activation and weight planes", Cin2);
     const int NT = Cout_pad == 16 ? 16 : (Cout_pad % 128 == 0 ? 128 : 64);
 
@@ -685,12 +840,33 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     p.taps = ksize * ksize;
     int tw = 1 << ilog2(W); if (tw > 16) tw = 16;
     int th = 1 << ilog2(H); if (th > 128 / tw) th = 128 / tw;
-    // halo mode: 3x3 over a map of at least 16 x 8 and wide output tiles; fixed 8 (w) x 16 (h) tile
+    // halo mode: maps of at least 16 x 8 and wide output tiles; fixed 8 (w) x 16 (h) tile
     static const int halo_env = getenv("DSEP_CONV_HALO") ? atoi(getenv("DSEP_CONV_HALO")) : 1;
-    const bool halo = halo_env != 0 && kBK == 64 && ksize == 3 && W >= 8 && H >= 16 && Cout_pad != 16;
+    const bool halo_ok = kBK == 64 && W >= 8 && H >= 16 && Cout_pad != 16;
+    const bool halo = halo_ok && (main_fused || short_fused || (halo_env != 0 && ksize == 3));
+    DSEP_REQUIRE(!(main_fused || short_fused) || halo_ok,
+                 "conv2d_fused: the in-kernel prologue needs a map of at least 16 x 8 and Cout >= 64 "
+                 "(got %dx%d, Cout_pad %d)", H, W, Cout_pad);
+    // all A patches of a launch come from ONE agent (TMA producer or worker warps): two agents sharing the
+    // patch ring could fall a whole mbarrier phase apart
+    DSEP_REQUIRE(Cin2 == 0 || main_fused == short_fused,
+                 "conv2d_fused: main and shortcut operands must both be fp32 (in-kernel prologue) or both planes");
+    if (main_fused) {
+        DSEP_REQUIRE(g->C0 > 0 && g->C0 % 64 == 0 && g->C1 >= 0 && g->C1 % 64 == 0 && g->C0 + g->C1 == Cin &&
+                         (g->C1 == 0 || g->x1 != nullptr),
+                     "conv2d_fused: main operand channels (%d + %d) must be multiples of 64 adding up to Cin=%d",
+                     g->C0, g->C1, Cin);
+        DSEP_REQUIRE((g->sc == nullptr) == (g->sh == nullptr), "conv2d_fused: sc and sh come together");
+    }
+    if (short_fused) {
+        DSEP_REQUIRE(g->S0 > 0 && g->S0 % 64 == 0 && g->S1 >= 0 && g->S1 % 64 == 0 && g->S0 + g->S1 == Cin2 &&
+                         (g->S1 == 0 || g->s1 != nullptr),
+                     "conv2d_fused: shortcut operand channels (%d + %d) must be multiples of 64 adding up to Cin2=%d",
+                     g->S0, g->S1, Cin2);
+    }
     if (halo) { tw = 8; th = 16; }
     const int tb = 128 / (tw * th);
-    DSEP_REQUIRE(stats == nullptr || (Cout_pad != 16 && tb == 1),
+    DSEP_REQUIRE(g->stats == nullptr || (Cout_pad != 16 && tb == 1),
                  "conv2d_tc: fused statistics need Cout >= 64 and 128-pixel tiles inside one batch entry "
                  "(got %dx%d, tile %dx%dx%d)", H, W, th, tw, tb);
     p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
@@ -700,8 +876,10 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
     p.kblocks = Cin / kBK;
     p.kblocks2 = Cin2 / kBK;
     p.passes = passes;
-    p.bias = bias; p.film = film; p.film_stride = film_stride; p.residual = residual;
-    p.scale = scale; p.acc_scale = acc_scale; p.out = out; p.stats = stats;
+    p.bias = g->bias; p.film = g->film; p.film_stride = g->film_stride; p.residual = g->residual;
+    p.scale = g->scale; p.acc_scale = g->acc_scale; p.out = g->out; p.stats = g->stats;
+    p.fx0 = g->x0; p.fx1 = g->x1; p.fC0 = g->C0; p.fC1 = g->C1; p.fsc = g->sc; p.fsh = g->sh; p.fact = g->act;
+    p.gx0 = g->s0; p.gx1 = g->s1; p.gC0 = g->S0; p.gC1 = g->S1;
     {
         static const int dbg = getenv("DSEP_CONV_DEBUG") ? atoi(getenv("DSEP_CONV_DEBUG")) : 0;
         p.debug = dbg;
@@ -709,42 +887,54 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
 
     ConvMaps m;
     int rc;
+    const bool patch3 = halo && ksize == 3;
     {
-        const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        const cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)(halo ? kPatchW : tw),
-                                    (cuuint32_t)(halo ? kPatchH : th), (cuuint32_t)tb};
         const cuuint64_t wdims[2] = {(cuuint64_t)Cin, (cuuint64_t)p.taps * Cout_pad};
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
         const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
-        if ((rc = make_map(&m.a_hi, a_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
-        if ((rc = make_map(&m.w_hi, w_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+        if ((rc = make_map(&m.w_hi, g->w_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         if (passes == 3) {
-            if ((rc = make_map(&m.a_lo, a_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
-            if ((rc = make_map(&m.w_lo, w_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+            if ((rc = make_map(&m.w_lo, g->w_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         } else {
-            m.a_lo = m.a_hi;
             m.w_lo = m.w_hi;
         }
+        if (!main_fused) {
+            const cuuint64_t adims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+            const cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+            const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)(patch3 ? kPatchW : tw),
+                                        (cuuint32_t)(patch3 ? kPatchH : th), (cuuint32_t)tb};
+            if ((rc = make_map(&m.a_hi, g->a_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
+            if (passes == 3) {
+                if ((rc = make_map(&m.a_lo, g->a_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
+            } else {
+                m.a_lo = m.a_hi;
+            }
+        } else {
+            m.a_hi = m.w_hi; m.a_lo = m.w_hi;     // unused by the kernel
+        }
     }
+    m.a2_hi = m.a_hi; m.a2_lo = m.a_lo; m.w2_hi = m.w_hi; m.w2_lo = m.w_lo;
     if (Cin2 > 0) {
-        const cuuint64_t adims[4] = {(cuuint64_t)Cin2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        const cuuint64_t astr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)W * Cin2 * 2, (cuuint64_t)H * W * Cin2 * 2};
-        const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
         const cuuint64_t wdims[2] = {(cuuint64_t)Cin2, (cuuint64_t)Cout_pad};
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin2 * 2};
         const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
-        if ((rc = make_map(&m.a2_hi, a2_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
-        if ((rc = make_map(&m.w2_hi, w2_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+        if ((rc = make_map(&m.w2_hi, g->w2_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         if (passes == 3) {
-            if ((rc = make_map(&m.a2_lo, a2_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
-            if ((rc = make_map(&m.w2_lo, w2_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
+            if ((rc = make_map(&m.w2_lo, g->w2_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         } else {
-            m.a2_lo = m.a2_hi;
             m.w2_lo = m.w2_hi;
         }
-    } else {
-        m.a2_hi = m.a_hi; m.a2_lo = m.a_lo; m.w2_hi = m.w_hi; m.w2_lo = m.w_lo;
+        if (!short_fused) {
+            const cuuint64_t adims[4] = {(cuuint64_t)Cin2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+            const cuuint64_t astr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)W * Cin2 * 2, (cuuint64_t)H * W * Cin2 * 2};
+            const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+            if ((rc = make_map(&m.a2_hi, g->a2_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
+            if (passes == 3) {
+                if ((rc = make_map(&m.a2_lo, g->a2_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
+            } else {
+                m.a2_lo = m.a2_hi;
+            }
+        }
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (halo) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);
@@ -753,4 +943,20 @@ extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, 
         case 64: return launch_conv<64, false>(m, p, s);
         default: return launch_conv<128, false>(m, p, s);
     }
+}
+
+extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,
+                              const void* w_hi, const void* w_lo, int Cout_pad, int ksize,
+                              const void* a2_hi, const void* a2_lo, int Cin2, const void* w2_hi,
+                              const void* w2_lo, const float* bias, const float* film, int film_stride,
+                              const float* residual, float scale, float acc_scale, float* out,
+                              int cout_store, double* stats, int passes, dsep_stream_t stream) {
+    dsep_conv_args g{};
+    g.a_hi = a_hi; g.a_lo = a_lo; g.B = B; g.H = H; g.W = W; g.Cin = Cin;
+    g.w_hi = w_hi; g.w_lo = w_lo; g.Cout_pad = Cout_pad; g.ksize = ksize;
+    g.a2_hi = a2_hi; g.a2_lo = a2_lo; g.Cin2 = Cin2; g.w2_hi = w2_hi; g.w2_lo = w2_lo;
+    g.bias = bias; g.film = film; g.film_stride = film_stride; g.residual = residual;
+    g.scale = scale; g.acc_scale = acc_scale; g.out = out; g.cout_store = cout_store; g.stats = stats;
+    g.passes = passes;
+    return dsep_conv2d_fused(&g, stream);
 }

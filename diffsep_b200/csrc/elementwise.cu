@@ -121,6 +121,21 @@ __device__ __forceinline__ void gn_tables(const double* __restrict__ st0, int C0
     __syncthreads();
 }
 
+// one block per batch entry: writes the tables to global memory for dsep_conv2d_fused's prologue
+__global__ void __launch_bounds__(256)
+gn_tables_kernel(const double* __restrict__ st0, int C0, const double* __restrict__ st1, int C1, int P, int groups,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ sc,
+                 float* __restrict__ sh) {
+    extern __shared__ float s_tab[];   // sc[Ct] | sh[Ct] | mean[64] | rstd[64]
+    const int Ct = C0 + C1, b = blockIdx.x;
+    gn_tables(st0, C0, st1, C1, b, groups, (double)P, gamma, beta, eps, s_tab, s_tab + Ct, s_tab + 2 * Ct,
+              s_tab + 2 * Ct + 64);
+    for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+        sc[static_cast<size_t>(b) * Ct + c] = s_tab[c];
+        sh[static_cast<size_t>(b) * Ct + c] = s_tab[Ct + c];
+    }
+}
+
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float4 affine_act(const float4 v, const float4 sc, const float4 sh, bool act) {
@@ -463,6 +478,18 @@ extern "C" int dsep_channel_stats(const float* x, int C, int B, int P, double* s
     dim3 grid(ceil_div(P, ppb), B);
     channel_stats_kernel<<<grid, 256, sizeof(double) * 2 * C, s>>>(x, C, P, ppb, stats);
     return check_launch("channel_stats_kernel");
+}
+
+extern "C" int dsep_gn_tables(const double* st0, int C0, const double* st1, int C1, int B, int P, int groups,
+                              const float* gamma, const float* beta, float eps, float* sc, float* sh,
+                              dsep_stream_t stream) {
+    DSEP_REQUIRE(st0 && gamma && beta && sc && sh && (C1 == 0 || st1), "gn_tables: null pointer");
+    DSEP_REQUIRE(B > 0 && P > 0 && B <= 65535, "gn_tables: empty tensor");
+    int rc = check_gn_shape("gn_tables", C0, C1, groups);
+    if (rc) return rc;
+    const size_t smem = sizeof(float) * (2 * (C0 + C1) + 128);
+    gn_tables_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(st0, C0, st1, C1, P, groups, gamma, beta, eps, sc, sh);
+    return check_launch("gn_tables_kernel");
 }
 
 extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x1, int C1,

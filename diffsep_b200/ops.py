@@ -81,6 +81,34 @@ def conv2d_tc(a: Split, B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store
     return out
 
 
+def conv2d_fused(B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store, a: Split = None, x0=None, C0=0, x1=None,
+                 C1=0, sc=None, sh=None, act=0, a2: Split = None, s0=None, S0=0, s1=None, S1=0, Cin2=0,
+                 w2: Split = None, bias=None, film=None, film_stride=0, residual=None, scale=1.0, acc_scale=1.0,
+                 stats=None, passes=3):
+    """dsep_conv2d_fused: the convolution with GroupNorm-apply / SiLU / concat / split of its operands
+    done in-kernel (x0[, x1] with sc, sh) instead of arriving as split planes (a)."""
+    _f32(out, "out"); _f32(bias, "bias"); _f32(film, "film"); _f32(residual, "residual")
+    _f32(x0, "x0"); _f32(x1, "x1"); _f32(s0, "s0"); _f32(s1, "s1"); _f32(sc, "sc"); _f32(sh, "sh")
+    g = _lib.ConvArgs(
+        ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(x0), ptr(x1), C0, C1, ptr(sc), ptr(sh), act,
+        B, H, W, Cin, ptr(w.hi), ptr(w.lo), cout_pad, ksize, ptr(a2.hi) if a2 else None,
+        ptr(a2.lo) if a2 else None, ptr(s0), ptr(s1), S0, S1, Cin2, ptr(w2.hi) if w2 else None,
+        ptr(w2.lo) if w2 else None, ptr(bias), film.data_ptr() if film is not None else None, film_stride,
+        ptr(residual), scale, acc_scale, ptr(out), cout_store, ptr(stats), passes)
+    try:
+        call("dsep_conv2d_fused", C.byref(g), stream())
+    except RuntimeError as e:
+        desc = {k: getattr(g, k) for k, t in g._fields_ if t is C.c_int or t is C.c_float}
+        desc.update({k: bool(getattr(g, k)) for k, t in g._fields_ if t is C.c_void_p})
+        raise RuntimeError(f"{e} :: {desc}") from e
+    return out
+
+
+def gn_tables(st0, C0, st1, C1, B, P, groups, gamma, beta, eps, sc, sh):
+    call("dsep_gn_tables", ptr(st0), C0, ptr(st1), C1, B, P, groups, ptr(gamma), ptr(beta), eps, ptr(sc), ptr(sh),
+         stream())
+
+
 def channel_stats(x, Cc, B, P, stats):
     if stats.dtype != torch.float64:
         raise ValueError("stats must be float64 [B, C, 2]")

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 2
+#define DSEP_ABI_VERSION 3
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -65,6 +65,45 @@ int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int 
                    const void* a2_hi, const void* a2_lo, int Cin2, const void* w2_hi, const void* w2_lo,
                    const float* bias, const float* film, int film_stride, const float* residual,
                    float scale, float acc_scale, float* out, int cout_store, double* stats, int passes,
+                   dsep_stream_t stream);
+
+/* Same convolution with the operand-producing passes folded in (the north-star fusion: one ResBlock
+ * = two launches).  Any field left NULL/0 selects the dsep_conv2d_tc behaviour for that operand.
+ *   main operand:     x0 != NULL  =>  A = act(x * sc[b,c] + sh[b,c]) of the fp32, channel-concatenated
+ *                     [x0 (C0 ch) | x1 (C1 ch)] (C0 + C1 == Cin), built in-kernel; sc/sh [B, Cin] come
+ *                     from dsep_gn_tables (NULL: identity), act 0 none / 1 SiLU; zero outside the image
+ *                     (the convolution pads the ACTIVATED tensor).  Replaces nn.GroupNorm + nn.SiLU +
+ *                     torch.cat in front of Conv_0 / Conv_1 / NIN_0..2 (layerspp.py:292-309, 76-82).
+ *   shortcut operand: s0 != NULL  =>  A2 = the raw fp32 [s0 (S0 ch) | s1 (S1 ch)] (S0 + S1 == Cin2).
+ * Needs a map of at least 16 x 8 pixels and Cout >= 64 (smaller maps: dsep_gn_act_split + dsep_conv2d_tc). */
+typedef struct {
+    const void *a_hi, *a_lo;            /* split planes [B,H,W,Cin], or NULL with x0 set            */
+    const float *x0, *x1;               /* fp32 activations [B,H,W,C0], [B,H,W,C1]                  */
+    int C0, C1;
+    const float *sc, *sh;               /* [B, Cin] affine of the in-kernel prologue                */
+    int act;
+    int B, H, W, Cin;
+    const void *w_hi, *w_lo;            /* [ksize*ksize, Cout_pad, Cin]                             */
+    int Cout_pad, ksize;
+    const void *a2_hi, *a2_lo;          /* shortcut planes [B,H,W,Cin2], or NULL with s0 set        */
+    const float *s0, *s1;
+    int S0, S1;
+    int Cin2;
+    const void *w2_hi, *w2_lo;          /* [Cout_pad, Cin2]                                         */
+    const float *bias, *film;
+    int film_stride;
+    const float* residual;
+    float scale, acc_scale;
+    float* out;
+    int cout_store;
+    double* stats;
+    int passes;
+} dsep_conv_args;
+int dsep_conv2d_fused(const dsep_conv_args* args, dsep_stream_t stream);
+/* Per-(batch entry, channel) GroupNorm scale / shift from per-channel sums of a (concatenated) input:
+ * sc = gamma * rstd[group], sh = beta - mean[group] * sc, so that GN(x) = x * sc + sh.  sc, sh: [B, C0+C1]. */
+int dsep_gn_tables(const double* st0, int C0, const double* st1, int C1, int B, int P, int groups,
+                   const float* gamma, const float* beta, float eps, float* sc, float* sh,
                    dsep_stream_t stream);
 
 /* x * prescale (fp32, n elements) -> split fp16 planes. */

@@ -38,7 +38,7 @@ def split(ops, x, prescale=1.0):
 def test_library_loaded_and_device_ok():
     from diffsep_b200 import _lib
     lib = _lib.load()
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 3
     assert lib.dsep_device_ok() == 1
 
 
@@ -133,6 +133,68 @@ def test_conv2d_tc_fused_shortcut_and_statistics(shape, passes):
     got = nchw(out).double()
     assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
     assert rel_l2(stats[..., 1].cpu(), (got * got).sum(dim=(2, 3))) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 24, 64, 64, 128, 3), (1, 32, 40, 128, 0, 128, 3), (1, 48, 16, 128, 128, 64, 3),
+                                   (2, 16, 16, 128, 0, 384, 1)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv2d_fused_prologue(shape, passes):
+    """dsep_conv2d_fused: conv(SiLU(GN(cat[x0, x1]))) [+ conv1x1(cat[x0, x1]) shortcut] with the
+    GroupNorm apply / SiLU / concat / fp16 split done by the conv kernel's worker warps (no operand
+    planes in HBM), vs float64.  1x1 case = the attention block's GN (no SiLU) + stacked q/k/v NIN."""
+    ops = _ops()
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, C0, C1, Cout, k = shape
+    Ct = C0 + C1
+    g = cases.gen(sum(shape) + 1)
+    x0 = torch.randn(B, C0, H, W, generator=g) * 1.3 + 0.2
+    x1 = torch.randn(B, C1, H, W, generator=g) * 0.7 - 0.1 if C1 else None
+    xcat = torch.cat([x0, x1], 1) if C1 else x0
+    gamma = 1 + 0.1 * torch.randn(Ct, generator=g)
+    beta = 0.1 * torch.randn(Ct, generator=g)
+    groups = min(Ct // 4, 32)
+    w = torch.randn(Cout, Ct, k, k, generator=g) / math.sqrt(Ct * k * k)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    act = 1 if k == 3 else 0
+    a_ref = F.group_norm(xcat.double(), groups, gamma.double(), beta.double(), eps=1e-6)
+    if act:
+        a_ref = a_ref * torch.sigmoid(a_ref)
+    ref = F.conv2d(a_ref, w.double(), b1.double(), padding=k // 2)
+    shortcut = None
+    if k == 3:
+        w2 = torch.randn(Cout, Ct, 1, 1, generator=g) / math.sqrt(Ct)
+        b2 = torch.randn(Cout, generator=g) * 0.1
+        shortcut = (w2, b2)
+        ref = (ref + F.conv2d(xcat.double(), w2.double(), b2.double())) / math.sqrt(2.0)
+    cw = ConvWeight(w, b1, DEV, shortcut=shortcut)
+    d0, d1 = cl(x0), (cl(x1) if C1 else None)
+    st0 = torch.empty(B, C0, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, C0, B, H * W, st0)
+    st1 = None
+    if C1:
+        st1 = torch.empty(B, C1, 2, dtype=torch.float64, device=DEV)
+        ops.channel_stats(d1, C1, B, H * W, st1)
+    sc = torch.empty(B, Ct, device=DEV)
+    sh = torch.empty(B, Ct, device=DEV)
+    ops.gn_tables(st0, C0, st1, C1, B, H * W, groups, gamma.to(DEV), beta.to(DEV), 1e-6, sc, sh)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    stats = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    kw = dict(s0=d0, S0=C0, s1=d1, S1=C1, Cin2=Ct, w2=cw.planes2, scale=1 / math.sqrt(2.0)) if k == 3 else {}
+    ops.conv2d_fused(B, H, W, Ct, cw.planes, cw.cout_pad, k, out, Cout, x0=d0, C0=C0, x1=d1, C1=C1, sc=sc, sh=sh,
+                     act=act, bias=cw.bias, acc_scale=cw.acc_scale, stats=stats, passes=passes, **kw)
+    torch.cuda.synchronize()
+    # up to 2560 accumulation steps into a truncating fp32 accumulator (shortcut terms first): < 2e-5
+    assert rel_l2(nchw(out), ref) < (2e-5 if passes == 3 else 1e-3)
+    got = nchw(out).double()
+    assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
+
+
+def test_conv2d_fused_rejects_small_maps():
+    ops = _ops()
+    w = ops.Split.zeros((9, 64, 64), DEV)
+    x = torch.zeros(1, 8, 8, 64, device=DEV)
+    with pytest.raises(ValueError):
+        ops.conv2d_fused(1, 8, 8, 64, w, 64, 3, torch.empty(1, 8, 8, 64, device=DEV), 64, x0=x, C0=64)
 
 
 def test_conv2d_tc_statistics_need_whole_tiles_per_batch_entry():
