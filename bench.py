@@ -268,17 +268,31 @@ def run_gpu(args):
 
 def dominant_kernel_roofline(model, dev, peaks, passes):
     """Times the level-0 ResBlock 3x3 conv (128 -> 128 at 256x256, batch 32: 57.6 % of the network's
-    FLOPs run at this shape) alone: 20 launches bracketed by CUDA events on the launching stream."""
+    FLOPs run at this shape) alone, exactly as the network launches it — GroupNorm-apply + SiLU + fp16
+    split prologue in-kernel, FiLM bias and next-GroupNorm statistics in the epilogue: 20 launches
+    bracketed by CUDA events on the launching stream."""
     from diffsep_b200 import ops
     bb = model.score_model.backbone
     rb = bb.down[0]["blocks"][0]
     B, H, W, Cc = B_PER_GPU, 256, 256, NF
-    a = ops.Split.empty((B, H, W, Cc), dev)
-    a.hi.normal_(); a.lo.normal_(std=1e-3)
+    x = torch.randn(B, H, W, Cc, device=dev)
+    sc = torch.ones(B, Cc, device=dev)
+    sh = torch.zeros(B, Cc, device=dev)
+    film = torch.zeros(B, Cc, device=dev)
+    stats = torch.zeros(B, Cc, 2, dtype=torch.float64, device=dev)
     out = torch.empty(B, H, W, Cc, device=dev)
     cw = rb["conv0"]
-    run = lambda: ops.conv2d_tc(a, B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, bias=cw.bias,
-                                acc_scale=cw.acc_scale, passes=passes)
+    if bb.fuse:
+        run = lambda: ops.conv2d_fused(B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, x0=x, C0=Cc, sc=sc, sh=sh,
+                                       act=1, bias=cw.bias, film=film, film_stride=Cc, acc_scale=cw.acc_scale,
+                                       stats=stats, passes=passes)
+        variant = "fp32 input, GN+SiLU+split prologue in-kernel, FiLM + GN statistics in the epilogue"
+    else:
+        a = ops.Split.empty((B, H, W, Cc), dev)
+        ops.split_f16(x, a)
+        run = lambda: ops.conv2d_tc(a, B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, bias=cw.bias, film=film,
+                                    film_stride=Cc, acc_scale=cw.acc_scale, stats=stats, passes=passes)
+        variant = "fp16 hi/lo operand planes by TMA, FiLM + GN statistics in the epilogue"
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -293,11 +307,16 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
     flops = 2.0 * B * H * W * 9 * Cc * Cc
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops", 1590.0)
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<128> (3x3, 128->128, 256x256, batch 32)",
+    traffic = None
+    tf = ROOT / "profiles" / "conv_traffic.json"      # dram bytes per launch from the committed ncu --set full capture
+    if tf.exists() and B == 32:
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    return {"bound": "tensor", "kernel": "conv_tc_kernel<128, halo> (3x3, 128->128, 256x256, batch %d): %s" % (B, variant),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "ms_per_launch": ms, "algorithmic_gflop_per_launch": flops / 1e9, "mma_passes": passes,
-            "traffic": None}
+            "issued_frac": passes * achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": 2 * 4.0 * B * H * W * Cc}
 
 
 def main():

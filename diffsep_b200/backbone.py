@@ -155,8 +155,11 @@ class NCSNppB200:
         ops.require_device()
         self.device = torch.device(device)
         self.nf, self.ch_in, self.ch_out, self.passes = nf, ch_in, ch_out, passes
-        # in-kernel GroupNorm/SiLU/concat prologue (dsep_conv2d_fused) where shapes allow
-        self.fuse = bool(int(os.environ.get("DSEP_FUSE", "1"))) if fuse is None else bool(fuse)
+        # in-kernel GroupNorm/SiLU/concat prologue (dsep_conv2d_fused) where shapes allow.  With three
+        # MMA passes per tile the worker warps have time to build the patches for free; with one pass
+        # they would become the bottleneck (measured), so that mode keeps the separate pass.
+        default_fuse = "1" if passes == 3 else "0"
+        self.fuse = bool(int(os.environ.get("DSEP_FUSE", default_fuse))) if fuse is None else bool(fuse)
         self.temb_dim = 4 * nf
         self._plans = {}
         self._load(params)

@@ -34,8 +34,19 @@ a = ops.Split.empty((B, H, W, CIN), dev)
 ops.split_f16(x, a)
 out = torch.empty(B, H, W, COUT, device=dev)
 res = torch.randn(B, H, W, COUT, device=dev) if with_res else None
-run = lambda: ops.conv2d_tc(a, B, H, W, CIN, cw.planes, cw.cout_pad, K, out, COUT, bias=cw.bias, residual=res,
-                            scale=0.7071 if with_res else 1.0, acc_scale=cw.acc_scale, passes=passes)
+with_stats = int(os.environ.get("DSEP_STATS", "0"))
+fused_in = int(os.environ.get("DSEP_FUSEDIN", "0"))
+stats = torch.zeros(B, COUT, 2, dtype=torch.float64, device=dev) if with_stats else None
+sc = torch.ones(B, CIN, device=dev)
+sh = torch.zeros(B, CIN, device=dev)
+if fused_in:
+    run = lambda: ops.conv2d_fused(B, H, W, CIN, cw.planes, cw.cout_pad, K, out, COUT, x0=x, C0=CIN, sc=sc, sh=sh,
+                                   act=1, bias=cw.bias, residual=res, scale=0.7071 if with_res else 1.0,
+                                   acc_scale=cw.acc_scale, stats=stats, passes=passes)
+else:
+    run = lambda: ops.conv2d_tc(a, B, H, W, CIN, cw.planes, cw.cout_pad, K, out, COUT, bias=cw.bias, residual=res,
+                                scale=0.7071 if with_res else 1.0, acc_scale=cw.acc_scale, passes=passes,
+                                stats=stats)
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -47,5 +58,6 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 fl = 2.0 * B * H * W * K * K * CIN * COUT
-print(f"conv {K}x{K} {CIN}->{COUT} {H}x{W} B={B} passes={passes} res={with_res}: {ms:.3f} ms  "
+print(f"conv {K}x{K} {CIN}->{COUT} {H}x{W} B={B} passes={passes} res={with_res} stats={with_stats} "
+      f"fused_in={fused_in}: {ms:.3f} ms  "
       f"{fl / ms / 1e9:.1f} TFLOP/s algorithmic, {passes * fl / ms / 1e9:.1f} TFLOP/s issued", flush=True)

@@ -1,2 +1,6 @@
-for d in 0 1 2 3; do echo "halo debug=$d"; DSEP_CONV_DEBUG=$d python tools/profile_conv.py; done
-for d in 0 1 2; do echo "halo p1 debug=$d"; DSEP_PASSES=1 DSEP_CONV_DEBUG=$d python tools/profile_conv.py; done
+python -m pytest tests/test_ops_gpu.py -q -k "conv2d" 2>&1 | tail -2
+DSEP_FUSEDIN=1 python tools/profile_conv.py
+DSEP_FUSEDIN=1 DSEP_STATS=1 DSEP_RES=1 python tools/profile_conv.py
+DSEP_FUSEDIN=1 DSEP_CONV_DEBUG=1 python tools/profile_conv.py
+DSEP_FUSEDIN=1 DSEP_CIN=256 python tools/profile_conv.py
+python tools/profile_eval.py
