@@ -129,14 +129,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
 
 // Builds one 64-channel A patch (PH x PW pixels, row = py * PW + px, 128-byte-swizzled K-major rows of
 // (hi, lo) fp16) from fp32 activations: y = act(x * sc[c] + sh[c]), zero outside the image (the conv
-// pads the ACTIVATED tensor).  Called by the 256 worker threads; wtid = 0..255.  Replaces the
+// pads the ACTIVATED tensor).  Called by the kBuilders builder threads; wtid = 0..319.  Replaces the
 // GroupNorm-apply + SiLU + split pass (and the channel concat) that used to run as its own kernel.
+constexpr int kBuilders = 320;   // the 8 worker warps + the 2 otherwise idle control warps
+
+// (hi, lo) fp16 pairs of two floats; out-of-range values saturate to +-65504 instead of becoming NaN
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - back.y), "f"(a - back.x));
+}
+
 template <int PW, int PH>
 __device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bool want_lo, const float* x0, int C0,
                                             const float* x1, int C1, int kb, const float* sc, const float* sh,
                                             int act, int b, int h_org, int w_org, int B, int H, int W, int wtid) {
     constexpr int kItems = PW * PH * 8;                    // (row, 8-channel chunk) pairs
-    constexpr int kIter = (kItems + 255) / 256;
+    constexpr int kIter = (kItems + kBuilders - 1) / kBuilders;
     const int j = wtid & 7;
     const int c = kb * 64 + j * 8;                          // first of this thread's 8 channels (concatenated)
     const float* src;
@@ -158,7 +167,7 @@ __device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bo
     bool inb[kIter];
 #pragma unroll
     for (int u = 0; u < kIter; ++u) {                        // all loads first: ~12 x 16 B in flight per thread
-        const int item = wtid + u * 256;
+        const int item = wtid + u * kBuilders;
         const int r = item >> 3;
         const int py = r / PW, px = r - py * PW;
         const int h = h_org + py, w = w_org + px;
@@ -173,7 +182,7 @@ __device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bo
     }
 #pragma unroll
     for (int u = 0; u < kIter; ++u) {
-        const int item = wtid + u * 256;
+        const int item = wtid + u * kBuilders;
         if (item >= kItems) break;
         const int r = item >> 3;
         float y[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
@@ -187,15 +196,7 @@ __device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bo
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float a = fminf(fmaxf(y[2 * e], -60000.0f), 60000.0f);
-            const float bq = fminf(fmaxf(y[2 * e + 1], -60000.0f), 60000.0f);
-            const __half2 h2 = __floats2half2_rn(a, bq);
-            const float2 back = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn(a - back.x, bq - back.y);
-            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
-            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
-        }
+        for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
         const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(j ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if (want_lo) *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -269,6 +270,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int tb_log2 = 7 - p.tw_log2 - p.th_log2;
     const int kiters = p.taps * p.kblocks + p.kblocks2;
     const uint32_t stage_tx = (three ? 2u : 1u) * static_cast<uint32_t>(kABytes + Cfg::kBBytes);
+
+    // builds, in ring order (shortcut K-blocks, then main), every A patch of one tile; run by kBuilders threads
+    auto build_tile_patches = [&](int item, int wtid, int& as_, uint32_t& aph) {
+        if constexpr (HALO) {
+            int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);
+            const int wt = r % p.tiles_w; r /= p.tiles_w;
+            const int ht = r % p.tiles_h; r /= p.tiles_h;
+            const int w0 = wt << 3, h0 = ht << 4, b0 = r;
+            const int total = p.kblocks + p.kblocks2;
+            for (int pi = 0; pi < total; ++pi) {
+                const bool second = pi < p.kblocks2;
+                mbar_wait(&aempty[as_], aph ^ 1u);
+                uint8_t* sa = stage_base + as_ * HaloCfg<NT>::kAStage;
+                if (!(p.debug & 2)) {
+                    if (second)
+                        build_patch<8, 16>(sa, sa + kPatchPlane, three, p.gx0, p.gC0, p.gx1, p.gC1, pi, nullptr, nullptr,
+                                           0, b0, h0, w0, p.B, p.H, p.W, wtid);
+                    else if (p.taps == 9)
+                        build_patch<kPatchW, kPatchH>(sa, sa + kPatchPlane, three, p.fx0, p.fC0, p.fx1, p.fC1,
+                                                      pi - p.kblocks2, p.fsc, p.fsh, p.fact, b0, h0 - 1, w0 - 1, p.B, p.H,
+                                                      p.W, wtid);
+                    else
+                        build_patch<8, 16>(sa, sa + kPatchPlane, three, p.fx0, p.fC0, p.fx1, p.fC1, pi - p.kblocks2,
+                                           p.fsc, p.fsh, p.fact, b0, h0, w0, p.B, p.H, p.W, wtid);
+                }
+                // generic-proxy writes -> visible to the tensor core's async proxy, then publish
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
+                if (wtid == 0) mbar_arrive(&afull[as_]);
+                if (++as_ == kHaloAStages) { as_ = 0; aph ^= 1u; }
+            }
+        }
+    };
 
     if (warp == 0 && lane == 0 && HALO) {
         // ------------------------------------------------------------------ TMA producer (halo mode)
@@ -476,6 +510,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
             umma_commit(&tfull[as]);          // accumulator complete -> epilogue
+        }
+    } else if (HALO && (warp == 2 || warp == 3)) {
+        // ------------------------------------------------------------------ spare warps: extra patch builders
+        if constexpr (HALO) {
+            if (p.fx0 != nullptr) {
+                const int wtid = 256 + static_cast<int>(threadIdx.x) - 64;
+                int as_ = 0;
+                uint32_t aph = 0;
+                for (int item = cluster_id; item < p.total_items; item += num_clusters)
+                    build_tile_patches(item, wtid, as_, aph);
+            }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
@@ -685,37 +730,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 uint32_t aph = 0;
                 int it = 0, prev_item = -1;
                 for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
-                    int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);
-                    const int wt = r % p.tiles_w; r /= p.tiles_w;
-                    const int ht = r % p.tiles_h; r /= p.tiles_h;
-                    const int w0 = wt << 3, h0 = ht << 4, b0 = r;
-                    const int total = p.kblocks + p.kblocks2;
-                    for (int pi = 0; pi < total; ++pi) {
-                        const bool second = pi < p.kblocks2;
-                        const bool mine = second ? p.gx0 != nullptr : p.fx0 != nullptr;
-                        mbar_wait(&aempty[as_], aph ^ 1u);      // stay phase-locked even on patches TMA fills
-                        if (mine) {
-                            uint8_t* sa = stage_base + as_ * HCfg::kAStage;
-                            if (!(p.debug & 2)) {
-                                if (second)
-                                    build_patch<8, 16>(sa, sa + kPatchPlane, three, p.gx0, p.gC0, p.gx1, p.gC1, pi,
-                                                       nullptr, nullptr, 0, b0, h0, w0, p.B, p.H, p.W, wtid);
-                                else if (p.taps == 9)
-                                    build_patch<kPatchW, kPatchH>(sa, sa + kPatchPlane, three, p.fx0, p.fC0, p.fx1, p.fC1,
-                                                                  pi - p.kblocks2, p.fsc, p.fsh, p.fact, b0, h0 - 1,
-                                                                  w0 - 1, p.B, p.H, p.W, wtid);
-                                else
-                                    build_patch<8, 16>(sa, sa + kPatchPlane, three, p.fx0, p.fC0, p.fx1, p.fC1,
-                                                       pi - p.kblocks2, p.fsc, p.fsh, p.fact, b0, h0, w0, p.B, p.H, p.W,
-                                                       wtid);
-                            }
-                            // generic-proxy writes -> visible to the tensor core's async proxy, then publish
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            asm volatile("bar.sync 1, 256;" ::: "memory");
-                            if (wtid == 0) mbar_arrive(&afull[as_]);
-                        }
-                        if (++as_ == NA) { as_ = 0; aph ^= 1u; }
-                    }
+                    build_tile_patches(item, wtid, as_, aph);
                     if (prev_item >= 0) do_epilogue(prev_item, it - 1);
                     prev_item = item;
                 }
