@@ -15,7 +15,6 @@ import argparse
 import sys
 from pathlib import Path
 
-import numpy as np
 import torch
 
 ROOT = Path(__file__).resolve().parent
@@ -83,23 +82,13 @@ def separate(mix, model, sampler_kwargs, device):
 
 
 def load_wav(path):
-    from scipy.io import wavfile
-    sr, data = wavfile.read(path)
-    if data.dtype.kind == "i":
-        data = data.astype(np.float32) / float(np.iinfo(data.dtype).max + 1)
-    elif data.dtype.kind == "u":
-        data = (data.astype(np.float32) - 128.0) / 128.0
-    data = np.asarray(data, dtype=np.float32)
-    if data.ndim == 1:
-        data = data[None]
-    else:
-        data = data.T
-    return torch.from_numpy(np.ascontiguousarray(data)), sr
+    from diffsep_b200.data import load_wav as _load
+    return _load(path)
 
 
 def save_wav(path, wav, sr):
-    from scipy.io import wavfile
-    wavfile.write(path, sr, wav.numpy().T.astype(np.float32))
+    from diffsep_b200.data import save_wav as _save
+    _save(path, wav, sr)
 
 
 def main(argv=None):
