@@ -533,7 +533,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         int run_b = -1, run_n0 = -1;
         auto flush_stats = [&]() {
             if constexpr (NT >= 64) {
-                if (p.stats == nullptr || run_b < 0 || run_b >= p.B || (lane >> 3) != 0) return;
+                if (p.stats == nullptr || run_b < 0) return;           // warp-uniform
+#pragma unroll
+                for (int c = 0; c < NT / 64; ++c) {                     // rows of the 4 lane groups -> lanes 0..7
+#pragma unroll
+                    for (int o = 8; o <= 16; o <<= 1) {
+                        run1[c].x += __shfl_xor_sync(0xffffffffu, run1[c].x, o);
+                        run1[c].y += __shfl_xor_sync(0xffffffffu, run1[c].y, o);
+                        run1[c].z += __shfl_xor_sync(0xffffffffu, run1[c].z, o);
+                        run1[c].w += __shfl_xor_sync(0xffffffffu, run1[c].w, o);
+                        run2[c].x += __shfl_xor_sync(0xffffffffu, run2[c].x, o);
+                        run2[c].y += __shfl_xor_sync(0xffffffffu, run2[c].y, o);
+                        run2[c].z += __shfl_xor_sync(0xffffffffu, run2[c].z, o);
+                        run2[c].w += __shfl_xor_sync(0xffffffffu, run2[c].w, o);
+                    }
+                }
+                if (run_b >= p.B || (lane >> 3) != 0) return;
 #pragma unroll
                 for (int c = 0; c < NT / 64; ++c) {
                     const int n = run_n0 + (ew >> 2) * (NT / 2) + c * 32 + (lane & 7) * 4;
@@ -634,6 +649,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     __syncwarp();
                     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.bias != nullptr && n_ok) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    // one batch entry per tile (every map of at least 128 pixels): FiLM joins the bias once
+                    const bool film_rows = p.film != nullptr && tb_log2 != 0;
+                    if (p.film != nullptr && tb_log2 == 0 && n_ok && b0 < p.B) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(
+                            p.film + static_cast<size_t>(b0) * p.film_stride + n));
+                        bz.x += f.x; bz.y += f.y; bz.z += f.z; bz.w += f.w;
+                    }
                     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -642,7 +664,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             float4 a = *reinterpret_cast<const float4*>(stg + row * 32 + ((q ^ (row & 7)) << 2));
                             a.x = fmaf(a.x, p.acc_scale, bz.x); a.y = fmaf(a.y, p.acc_scale, bz.y);
                             a.z = fmaf(a.z, p.acc_scale, bz.z); a.w = fmaf(a.w, p.acc_scale, bz.w);
-                            if (p.film != nullptr) {
+                            if (film_rows) {
                                 const int bi = b0 + ((wq * 32 + row) >> (p.tw_log2 + p.th_log2));
                                 const float4 f = __ldg(reinterpret_cast<const float4*>(
                                     p.film + static_cast<size_t>(bi) * p.film_stride + n));
@@ -660,14 +682,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         }
                     }
                     if (p.stats != nullptr) {
-                        // all 32 rows of this warp belong to one batch entry (host guarantees H*W >= 128)
-#pragma unroll
-                        for (int o = 8; o <= 16; o <<= 1) {
-                            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-                            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
-                            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
-                            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
-                        }
+                        // all 32 rows of this warp belong to one batch entry (host guarantees H*W >= 128);
+                        // the cross-lane reduction waits until the flush
                         run1[c].x += s1.x; run1[c].y += s1.y; run1[c].z += s1.z; run1[c].w += s1.w;
                         run2[c].x += s2.x; run2[c].y += s2.y; run2[c].z += s2.z; run2[c].w += s2.w;
                     }
