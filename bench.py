@@ -36,19 +36,30 @@ sys.path.insert(0, str(ROOT / "tests" / "golden"))
 import torch  # noqa: E402
 
 FS, SECONDS, N_STEPS, CORR_STEPS, SNR, NF = 8000, 4, 30, 1, 0.5, 128
-T = FS * SECONDS
-B_PER_GPU = int(os.environ.get("DSEP_BENCH_BATCH", "32"))
-GFLOP_PER_EVAL = 532.891          # per sample per evaluation at 256x256, nf=128
-NFE = N_STEPS * (CORR_STEPS + 1)
+B_DEFAULT, GFLOP_PER_EVAL, PRIOR, WORKLOAD = 32, 532.891, False, "configs[1]"   # GFLOP/sample/eval: SURVEY.md §8d
 METRIC = "separated utterances/sec (4 s, 8 kHz, 2-spk, N=30 PC steps)"
+# The driver's contract is configs[1] (the default).  The other single-GPU configurations of BASELINE.json can
+# be timed for the record with DSEP_BENCH_WORKLOAD; they print the same line with their own `config`.
+_W = os.environ.get("DSEP_BENCH_WORKLOAD", "")
+if _W == "configs[3]":      # enhancement: 16 kHz, PriorMixSDE, 4 s -> [B,6,256,512]
+    FS, B_DEFAULT, GFLOP_PER_EVAL, PRIOR, WORKLOAD = 16000, 16, 1066.173, True, _W
+    METRIC = "enhanced utterances/sec (4 s, 16 kHz, PriorMixSDE, N=30 PC steps)"
+elif _W == "configs[4]":    # long form: 30 s, N=50, 2 corrector steps -> [B,6,256,1920]
+    SECONDS, N_STEPS, CORR_STEPS, B_DEFAULT, GFLOP_PER_EVAL, WORKLOAD = 30, 50, 2, 8, 4006.432, _W
+    METRIC = "separated utterances/sec (30 s, 8 kHz, 2-spk, N=50 PC steps, 2 corrector steps)"
+T = FS * SECONDS
+B_PER_GPU = int(os.environ.get("DSEP_BENCH_BATCH", str(B_DEFAULT)))
+NFE = N_STEPS * (CORR_STEPS + 1)
 
 
 def config_dict(n_gpus):
     return {
-        "workload": f"configs[1]: batch={B_PER_GPU} x 4 s 8 kHz 2-spk mixtures per GPU, N=30, 1 corrector step, "
-                    f"snr=0.5, NCSN++ nf=128 (60 score evaluations of [{B_PER_GPU},6,256,256])",
+        "workload": f"{WORKLOAD}: batch={B_PER_GPU} x {SECONDS} s {FS // 1000} kHz mixtures per GPU, N={N_STEPS}, "
+                    f"{CORR_STEPS} corrector step(s), snr=0.5, NCSN++ nf=128 ({NFE} score evaluations of "
+                    f"[{B_PER_GPU},6,256,{-(-(1 + (T + 382) // 128) // 64) * 64}])",
         "global_batch": B_PER_GPU * n_gpus, "samples": T, "n_fft": 510, "hop": 128, "N": N_STEPS,
-        "corrector_steps": CORR_STEPS, "snr": SNR, "nf": NF, "sde": "MixSDE", "predictor": "reverse_diffusion",
+        "corrector_steps": CORR_STEPS, "snr": SNR, "nf": NF, "sde": "PriorMixSDE" if PRIOR else "MixSDE",
+        "predictor": "reverse_diffusion",
         "corrector": "ald2", "passes": int(os.environ.get("DSEP_PASSES", "3")),
         "l2": "working set (>4 GB of activations per evaluation) exceeds the 126 MB L2; no flush needed",
         "parallelism": f"dp{n_gpus} (utterance sharding, one all-gather of outputs)",
@@ -69,7 +80,7 @@ def cpu_sample(n_evals_N, threads):
     torch.set_num_threads(threads)
     params = ow.make_backbone_params(nf=NF, seed=0)
     mix, _, _ = sd.normalize_batch(synthetic_batch(0, 1))
-    p = sd.MixSDEParams(N=n_evals_N)
+    p = sd.MixSDEParams(N=n_evals_N, prior=PRIOR)
     noises = cases.sampler_noises(1, T, n_evals_N, CORR_STEPS)
 
     def score_fn(x, t, m):
@@ -168,7 +179,13 @@ def run_gpu(args):
     ops.require_device()
     passes = int(os.environ.get("DSEP_PASSES", "3"))
 
-    model = DiffSepModel(DEFAULT_CONFIG, device=dev, passes=passes,
+    import copy
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg["model"]["fs"] = FS
+    if PRIOR:
+        cfg["model"]["sde"] = {"_target_": "sdes.sdes.PriorMixSDE", "ndim": 2, "d_lambda": 2.0, "sigma_min": 0.05,
+                               "sigma_max": 0.5, "N": 30, "avg_len": 510}
+    model = DiffSepModel(cfg, device=dev, passes=passes,
                          score_state_dict=ow.make_score_model_state_dict(nf=NF, seed=0))
     B = B_PER_GPU
     host_mix = synthetic_batch(rank * B, B).pin_memory()
@@ -242,10 +259,10 @@ def run_gpu(args):
         sustained = peaks.get("bf16_tflops_sustained", 1400.0)
         roof["step"] = {"achieved": step_tflops, "peak": sustained, "unit": "TFLOP/s",
                         "frac": step_tflops / sustained,
-                        "note": "whole job: algorithmic FLOPs (532.891 GFLOP/sample/eval x 60) / wall, per GPU, "
-                                "vs sustained measured bf16 peak"}
+                        "note": f"whole job: algorithmic FLOPs ({GFLOP_PER_EVAL} GFLOP/sample/eval x {NFE}) / wall, "
+                                "per GPU, vs sustained measured bf16 peak"}
         threads = os.cpu_count() or 1
-        cpu_dt, cpu_utt_s, cpu_nfe = cpu_sample(3, threads)
+        cpu_dt, cpu_utt_s, cpu_nfe = cpu_sample(3 if WORKLOAD == "configs[1]" else 1, threads)
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -256,8 +273,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clock_info, "roofline": roof,
             "cpu_baseline": {"value": cpu_utt_s, "unit": "utt/s", "cores": threads, "kind": "port",
-                             "sample": f"1 utterance x {cpu_nfe} of {NFE} score evaluations (N=3 PC steps) through "
-                                       f"the CPU oracle in {cpu_dt:.1f} s, scaled x{NFE // cpu_nfe}"},
+                             "sample": f"1 utterance x {cpu_nfe} of {NFE} score evaluations through "
+                                       f"the CPU oracle in {cpu_dt:.1f} s, scaled x{NFE / cpu_nfe:g}"},
         }
     if world > 1:
         dist.barrier()
