@@ -13,7 +13,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / "libdsep.so"
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -57,7 +57,9 @@ PROTOTYPES = {
     "dsep_istft_ola": [_p, _p, _i, _i, _i, _i, _p, _p],
     "dsep_sde_prior": [C.POINTER(SdeParams), _p, _p, _p, _u64, _u64, _i, _i, _p, _p],
     "dsep_sde_corrector": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
-    "dsep_sde_predictor": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
+    "dsep_sde_predictor": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _i, _p, _p, _p],
+    "dsep_sde_corrector_ald": [C.POINTER(SdeParams), _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
+    "dsep_sde_corrector_langevin": [_p, _p, _p, _f, _i, _i, _p, _p, _p, _p],
     "dsep_sigma_mix": [_p, _i, _i, _i, _p, _p],
     "dsep_normalize": [_p, _i, _i, _p, _p, _p, _p],
     "dsep_scale_output": [_p, _p, _i, _i, _i, _p, _p],

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(256)
 sde_update_kernel(const dsep_sde_params p, const float* __restrict__ x, const float* __restrict__ score,
                   const float* __restrict__ mix, const float* __restrict__ tvec,
                   const float* __restrict__ sigma_mix, const float* __restrict__ noise, uint64_t seed,
-                  uint64_t offset, float coef, int T, float* __restrict__ x_out, float* __restrict__ x_mean) {
+                  uint64_t offset, float coef, int flag, int T, float* __restrict__ x_out,
+                  float* __restrict__ x_mean) {
     const int b = blockIdx.y;
     const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (t0 >= T) return;
@@ -162,20 +163,33 @@ sde_update_kernel(const dsep_sde_params p, const float* __restrict__ x, const fl
             o0.v[i] = m0.v[i] + c1 * n0;
             o1.v[i] = m1.v[i] + c1 * n1;
         }
+    } else if (MODE == 3) {
+        // ald (original annealed Langevin, correctors.py:58-91): std = sqrt of the first-row sum of the
+        // covariance = sqrt(ev1); step = 2 (snr std)^2; x_mean = x + step s; x' = x_mean + sqrt(2 step) z
+        const float step = 2.0f * (coef * sc.s1) * (coef * sc.s1), nz = sqrtf(2.0f * step);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            m0.v[i] = x0.v[i] + step * s0.v[i];
+            m1.v[i] = x1.v[i] + step * s1.v[i];
+            o0.v[i] = m0.v[i] + nz * z0.v[i];
+            o1.v[i] = m1.v[i] + nz * z1.v[i];
+        }
     } else {
-        // reverse diffusion: f = -lambda (x - xbar) dt, G = g sqrt(dt);  x_mean = x - (f - G^2 s);
-        // x' = x_mean + G z                                                     (coef = dt)
+        // reverse diffusion: f = -lambda (x - xbar) dt, G = g sqrt(dt);  x_mean = x - (f - c G^2 s);
+        // x' = x_mean + G z   (coef = dt).  probability flow (flag): c = 1/2 and no noise
+        // (sdes.py:143-152,167-170); otherwise c = 1.
         const float dt = coef, sq = sqrtf(dt);
+        const float cs = flag ? 0.5f : 1.0f, cz = flag ? 0.0f : 1.0f;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const float xb = 0.5f * (x0.v[i] + x1.v[i]);
             const float G = sc.g * sm.v[i] * sq;
             const float f0 = -p.d_lambda * (x0.v[i] - xb) * dt;
             const float f1 = -p.d_lambda * (x1.v[i] - xb) * dt;
-            m0.v[i] = x0.v[i] - (f0 - G * G * s0.v[i]);
-            m1.v[i] = x1.v[i] - (f1 - G * G * s1.v[i]);
-            o0.v[i] = m0.v[i] + G * z0.v[i];
-            o1.v[i] = m1.v[i] + G * z1.v[i];
+            m0.v[i] = x0.v[i] - (f0 - cs * G * G * s0.v[i]);
+            m1.v[i] = x1.v[i] - (f1 - cs * G * G * s1.v[i]);
+            o0.v[i] = m0.v[i] + cz * G * z0.v[i];
+            o1.v[i] = m1.v[i] + cz * G * z1.v[i];
         }
     }
     stv<VEC>(x_out + e0, o0);
@@ -271,6 +285,39 @@ scale_output_kernel(const float* __restrict__ mix, const float* __restrict__ sep
     for (int i = threadIdx.x; i < T; i += blockDim.x) dst[i] = alpha * s[i];
 }
 
+// ---------------------------------------------------------------- LangevinCorrector (correctors.py:35-55)
+// norms[0][b] = ||score_b||, norms[1][b] = ||noise_b||; step = 2 (snr mean_b||noise_b|| / mean_b||score_b||)^2
+// couples the batch entries through the two batch means, exactly like the reference.
+__global__ void __launch_bounds__(1024)
+item_norms_kernel(const float* __restrict__ score, const float* __restrict__ noise, int n, float* __restrict__ norms) {
+    __shared__ double s_red[32];
+    const float* src = (blockIdx.y == 0 ? score : noise) + static_cast<int64_t>(blockIdx.x) * n;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ss += static_cast<double>(src[i]) * src[i];
+    ss = block_sum(ss, s_red);
+    if (threadIdx.x == 0) norms[blockIdx.y * gridDim.x + blockIdx.x] = static_cast<float>(sqrt(ss));
+}
+
+__global__ void __launch_bounds__(256)
+langevin_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ noise,
+                const float* __restrict__ norms, float snr, int B, int64_t total, float* __restrict__ x_out,
+                float* __restrict__ x_mean) {
+    __shared__ float s_step;
+    if (threadIdx.x == 0) {
+        float g = 0.f, z = 0.f;
+        for (int b = 0; b < B; ++b) { g += norms[b]; z += norms[B + b]; }
+        const float r = snr * (z / B) / (g / B);
+        s_step = r * r * 2.0f;
+    }
+    __syncthreads();
+    const float step = s_step, nz = sqrtf(step * 2.0f);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float m = x[i] + step * score[i];
+        x_mean[i] = m;
+        x_out[i] = m + nz * noise[i];
+    }
+}
+
 __global__ void randn_kernel(float* __restrict__ z, int64_t n, uint64_t seed, uint64_t offset) {
     const int64_t quads = (n + 3) / 4;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < quads;
@@ -285,7 +332,7 @@ __global__ void randn_kernel(float* __restrict__ z, int64_t n, uint64_t seed, ui
 template <int MODE>
 static int launch_update(const dsep_sde_params* p, const float* x, const float* score, const float* mix,
                          const float* t, const float* sigma_mix, const float* noise, uint64_t seed,
-                         uint64_t offset, float coef, int B, int T, float* x_out, float* x_mean,
+                         uint64_t offset, float coef, int flag, int B, int T, float* x_out, float* x_mean,
                          cudaStream_t s) {
     auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec = (T % 4 == 0) && aligned(x) && aligned(score) && aligned(mix) && aligned(sigma_mix) &&
@@ -293,11 +340,11 @@ static int launch_update(const dsep_sde_params* p, const float* x, const float* 
     if (vec) {
         dim3 grid(ceil_div(T / 4, 256), B);
         sde_update_kernel<MODE, 4><<<grid, 256, 0, s>>>(*p, x, score, mix, t, sigma_mix, noise, seed, offset,
-                                                        coef, T, x_out, x_mean);
+                                                        coef, flag, T, x_out, x_mean);
     } else {
         dim3 grid(ceil_div(T, 256), B);
         sde_update_kernel<MODE, 1><<<grid, 256, 0, s>>>(*p, x, score, mix, t, sigma_mix, noise, seed, offset,
-                                                        coef, T, x_out, x_mean);
+                                                        coef, flag, T, x_out, x_mean);
     }
     return check_launch("sde_update_kernel");
 }
@@ -319,7 +366,7 @@ extern "C" int dsep_sde_prior(const dsep_sde_params* p, const float* mix, const 
     int rc = check_sde("sde_prior", p, B, T);
     if (rc) return rc;
     DSEP_REQUIRE(mix && x, "sde_prior: null pointer");
-    return launch_update<0>(p, nullptr, nullptr, mix, nullptr, sigma_mix, noise, seed, offset, 0.f, B, T, x,
+    return launch_update<0>(p, nullptr, nullptr, mix, nullptr, sigma_mix, noise, seed, offset, 0.f, 0, B, T, x,
                             nullptr, (cudaStream_t)stream);
 }
 
@@ -330,20 +377,46 @@ extern "C" int dsep_sde_corrector(const dsep_sde_params* p, const float* x, cons
     int rc = check_sde("sde_corrector", p, B, T);
     if (rc) return rc;
     DSEP_REQUIRE(x && score && t && x_out, "sde_corrector: null pointer");
-    return launch_update<1>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, snr, B, T, x_out, x_mean,
+    return launch_update<1>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, snr, 0, B, T, x_out, x_mean,
                             (cudaStream_t)stream);
 }
 
 extern "C" int dsep_sde_predictor(const dsep_sde_params* p, const float* x, const float* score,
                                   const float* t, const float* sigma_mix, const float* noise, uint64_t seed,
-                                  uint64_t offset, float dt, int B, int T, float* x_out, float* x_mean,
-                                  dsep_stream_t stream) {
+                                  uint64_t offset, float dt, int probability_flow, int B, int T, float* x_out,
+                                  float* x_mean, dsep_stream_t stream) {
     int rc = check_sde("sde_predictor", p, B, T);
     if (rc) return rc;
     DSEP_REQUIRE(x && score && t && x_out, "sde_predictor: null pointer");
     DSEP_REQUIRE(dt > 0.f, "sde_predictor: dt must be positive");
-    return launch_update<2>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, dt, B, T, x_out, x_mean,
+    return launch_update<2>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, dt, probability_flow ? 1 : 0, B, T,
+                            x_out, x_mean,
                             (cudaStream_t)stream);
+}
+
+extern "C" int dsep_sde_corrector_ald(const dsep_sde_params* p, const float* x, const float* score,
+                                      const float* t, const float* noise, uint64_t seed, uint64_t offset,
+                                      float snr, int B, int T, float* x_out, float* x_mean,
+                                      dsep_stream_t stream) {
+    int rc = check_sde("sde_corrector_ald", p, B, T);
+    if (rc) return rc;
+    DSEP_REQUIRE(x && score && t && x_out, "sde_corrector_ald: null pointer");
+    return launch_update<3>(p, x, score, nullptr, t, nullptr, noise, seed, offset, snr, 0, B, T, x_out, x_mean,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int dsep_sde_corrector_langevin(const float* x, const float* score, const float* noise, float snr,
+                                           int B, int n, float* norms, float* x_out, float* x_mean,
+                                           dsep_stream_t stream) {
+    DSEP_REQUIRE(x && score && noise && norms && x_out && x_mean, "sde_corrector_langevin: null pointer");
+    DSEP_REQUIRE(B > 0 && B <= 4096 && n > 0, "sde_corrector_langevin: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    item_norms_kernel<<<dim3(B, 2), 1024, 0, s>>>(score, noise, n, norms);
+    const int64_t total = (int64_t)B * n;
+    int64_t blocks = (total + 1023) / 1024;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    langevin_kernel<<<(int)blocks, 256, 0, s>>>(x, score, noise, norms, snr, B, total, x_out, x_mean);
+    return check_launch("langevin_kernel");
 }
 
 extern "C" int dsep_sigma_mix(const float* mix, int B, int T, int avg_len, float* sigma, dsep_stream_t stream) {

@@ -206,9 +206,20 @@ def sde_corrector(p, x, score, t, sigma_mix, noise, seed, offset, snr, B, T, x_o
          ptr(sigma_mix), ptr(_f32(noise, "noise")), seed, offset, snr, B, T, ptr(x_out), ptr(x_mean), stream())
 
 
-def sde_predictor(p, x, score, t, sigma_mix, noise, seed, offset, dt, B, T, x_out, x_mean):
+def sde_predictor(p, x, score, t, sigma_mix, noise, seed, offset, dt, B, T, x_out, x_mean, probability_flow=False):
     call("dsep_sde_predictor", C.byref(p), ptr(_f32(x, "x")), ptr(_f32(score, "score")), ptr(_f32(t, "t")),
-         ptr(sigma_mix), ptr(_f32(noise, "noise")), seed, offset, dt, B, T, ptr(x_out), ptr(x_mean), stream())
+         ptr(sigma_mix), ptr(_f32(noise, "noise")), seed, offset, dt, int(bool(probability_flow)), B, T, ptr(x_out),
+         ptr(x_mean), stream())
+
+
+def sde_corrector_ald(p, x, score, t, noise, seed, offset, snr, B, T, x_out, x_mean):
+    call("dsep_sde_corrector_ald", C.byref(p), ptr(_f32(x, "x")), ptr(_f32(score, "score")), ptr(_f32(t, "t")),
+         ptr(_f32(noise, "noise")), seed, offset, snr, B, T, ptr(x_out), ptr(x_mean), stream())
+
+
+def sde_corrector_langevin(x, score, noise, snr, B, n, norms, x_out, x_mean):
+    call("dsep_sde_corrector_langevin", ptr(_f32(x, "x")), ptr(_f32(score, "score")), ptr(_f32(noise, "noise")), snr,
+         B, n, ptr(norms), ptr(x_out), ptr(x_mean), stream())
 
 
 def sigma_mix(mix, B, T, avg_len, out):

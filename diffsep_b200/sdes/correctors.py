@@ -1,11 +1,15 @@
-"""Corrector plugins (reference ``sdes/correctors.py:11-141``).  ``ald2`` — the one the CLIs
-hard-code (``separate.py:87-92``) — is implemented as one fused kernel per step; ``none`` keeps the
-reference's behaviour.  ``langevin`` / ``ald`` are outside the hot path."""
+"""Corrector plugins (reference ``sdes/correctors.py:11-141``): ``ald2`` — the one the CLIs hard-code
+(``separate.py:87-92``) —, ``ald`` and ``langevin`` are one fused kernel per step (``langevin`` plus a
+norm reduction); ``none`` keeps the reference's behaviour."""
 from __future__ import annotations
 
 import abc
 
+import torch
+
+from .. import ops
 from ..utils.registry import Registry
+from . import noise as _noise
 from . import sdes
 
 CorrectorRegistry = Registry("Corrector")
@@ -42,6 +46,48 @@ class AnnealedLangevinDynamics2(Corrector):
         for _ in range(self.n_steps):
             grad = self.score_fn(x, t, *args)
             x, x_mean = self.sde.corrector_update(x, grad, t, args[0], self.snr)
+        return x, x_mean
+
+
+@CorrectorRegistry.register("ald")
+class AnnealedLangevinDynamics(Corrector):
+    """The original annealed Langevin dynamics corrector of NCSN (correctors.py:58-91): step size
+    2 (snr std)^2 with std the scalar marginal standard deviation; MixSDE only, like the reference."""
+
+    def __init__(self, sde, score_fn, snr, n_steps):
+        super().__init__(sde, score_fn, snr, n_steps)
+        if not isinstance(sde, sdes.MixSDE):
+            raise NotImplementedError(f"SDE class {sde.__class__.__name__} not yet supported.")
+        self.sde = sde
+
+    def update_fn(self, x, t, *args, **kwargs):
+        x_mean = x
+        for _ in range(self.n_steps):
+            grad = self.score_fn(x, t, *args)
+            x, x_mean = self.sde.ald_update(x, grad, t, self.snr)
+        return x, x_mean
+
+
+@CorrectorRegistry.register("langevin")
+class LangevinCorrector(Corrector):
+    """Langevin corrector of score_sde (correctors.py:35-55): the step size comes from the batch means
+    of the per-entry score and noise norms, so batch entries are coupled (do not shard a batch across
+    GPUs with it if results must match the single-GPU run)."""
+
+    def update_fn(self, x, t, *args, **kwargs):
+        x_mean = x
+        B = x.shape[0]
+        n = x[0].numel()
+        for _ in range(self.n_steps):
+            grad = self.score_fn(x, t, *args)
+            z, seed, off = _noise.SOURCE.next(x.shape, x.device)
+            if z is None:
+                z = ops.randn(torch.empty_like(x), seed, off)
+            norms = torch.empty(2, B, device=x.device, dtype=torch.float32)
+            x_out, x_mean = torch.empty_like(x), torch.empty_like(x)
+            ops.sde_corrector_langevin(x.contiguous(), grad.contiguous(), z, float(self.snr), B, n, norms, x_out,
+                                       x_mean)
+            x = x_out
         return x, x_mean
 
 

@@ -15,7 +15,9 @@ class Predictor(abc.ABC):
     def __init__(self, sde, score_fn, probability_flow=False):
         super().__init__()
         self.sde = sde
-        self.rsde = sde.reverse(score_fn, probability_flow=probability_flow)
+        # like the reference (predictors.py:13-18) the flag is stored but NOT forwarded to reverse():
+        # probability_flow=True leaves the predictors unchanged (pinned by tests/golden/plugins.npz)
+        self.rsde = sde.reverse(score_fn)
         self.score_fn = score_fn
         self.probability_flow = probability_flow
 

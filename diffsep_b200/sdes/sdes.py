@@ -72,27 +72,35 @@ class SDE:
                           x_out, x_mean)
         return x_out, x_mean
 
-    def predictor_update(self, x, score, t, y, dt):
-        """reverse-diffusion / Euler-Maruyama step (predictors.py:60-66, sdes.py:93-107,163-171)."""
+    def predictor_update(self, x, score, t, y, dt, probability_flow=False):
+        """reverse-diffusion / Euler-Maruyama step (predictors.py:39-66, sdes.py:93-107,163-171); with
+        ``probability_flow`` the score term is halved and the noise dropped (sdes.py:143-152,167-170) —
+        a noise tensor is still drawn, as the reference's ``randn_like`` is."""
         self._check(x, y)
         B, _, T = x.shape
         x_out, x_mean = torch.empty_like(x), torch.empty_like(x)
         z, seed, off = _noise.SOURCE.next(x.shape, x.device)
         ops.sde_predictor(self._params(), x, score, t, self._sigma_mix(y), z, seed, off, float(dt), B, T,
-                          x_out, x_mean)
+                          x_out, x_mean, probability_flow=probability_flow)
+        return x_out, x_mean
+
+    def ald_update(self, x, score, t, snr):
+        """original annealed Langevin step (correctors.py:58-91), MixSDE only."""
+        B, _, T = x.shape
+        x_out, x_mean = torch.empty_like(x), torch.empty_like(x)
+        z, seed, off = _noise.SOURCE.next(x.shape, x.device)
+        ops.sde_corrector_ald(self._params(), x, score, t, z, seed, off, float(snr), B, T, x_out, x_mean)
         return x_out, x_mean
 
     def reverse(self, score_fn, probability_flow=False):
-        if probability_flow:
-            raise NotImplementedError("probability_flow=True is not on the DiffSep inference path")
-        return RSDE(self, score_fn)
+        return RSDE(self, score_fn, probability_flow)
 
 
 class RSDE:
     """Reverse-time SDE handle (reference sdes.py:109-173), reduced to what predictors use."""
 
-    def __init__(self, sde, score_fn):
-        self.sde, self.score_fn = sde, score_fn
+    def __init__(self, sde, score_fn, probability_flow=False):
+        self.sde, self.score_fn, self.probability_flow = sde, score_fn, probability_flow
         self.N = sde.N
 
     @property
@@ -101,7 +109,8 @@ class RSDE:
 
     def step(self, x, t, *args, dt=None):
         score = self.score_fn(x, t, *args)
-        return self.sde.predictor_update(x, score, t, args[0], 1.0 / self.sde.N if dt is None else dt)
+        return self.sde.predictor_update(x, score, t, args[0], 1.0 / self.sde.N if dt is None else dt,
+                                         probability_flow=self.probability_flow)
 
 
 @SDERegistry.register("mix")

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 3
+#define DSEP_ABI_VERSION 4
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -207,8 +207,9 @@ int dsep_istft_ola(const float* frames_t, const float* window, int B, int C, int
  * are drawn in-kernel (Philox4x32-10, Box-Muller) from (seed, offset).
  * prior:      x = 0.5 mix + L(T) z                         (sdes/sdes.py:334-346, 564-587)
  * corrector:  xm = x + 2 snr^2 L L score ; x' = xm + 2 snr L z   (sdes/correctors.py:109-128)
- * predictor:  xm = x + lambda dt (x - mean_c x) + G^2 score ; x' = xm + G z, G = g(t) sqrt(dt)
- *             (sdes/predictors.py:60-66, sdes/sdes.py:93-107,163-171,275-284) */
+ * predictor:  xm = x + lambda dt (x - mean_c x) + c G^2 score ; x' = xm + G z, G = g(t) sqrt(dt)
+ *             (sdes/predictors.py:39-66, sdes/sdes.py:93-107,163-171,275-284); probability_flow: c = 1/2
+ *             and no noise (sdes.py:143-152,167-170), else c = 1 */
 typedef struct {
     float d_lambda, sigma_min, sigma_max, T_end;
 } dsep_sde_params;
@@ -220,7 +221,19 @@ int dsep_sde_corrector(const dsep_sde_params* p, const float* x, const float* sc
                        float snr, int B, int T, float* x_out, float* x_mean, dsep_stream_t stream);
 int dsep_sde_predictor(const dsep_sde_params* p, const float* x, const float* score, const float* t,
                        const float* sigma_mix, const float* noise, uint64_t seed, uint64_t offset,
-                       float dt, int B, int T, float* x_out, float* x_mean, dsep_stream_t stream);
+                       float dt, int probability_flow, int B, int T, float* x_out, float* x_mean,
+                       dsep_stream_t stream);
+/* ald, the original annealed Langevin corrector (sdes/correctors.py:58-91; MixSDE only):
+ * std = sqrt(first-row sum of the covariance) = sqrt(ev1(t)); step = 2 (snr std)^2;
+ * xm = x + step score ; x' = xm + sqrt(2 step) z. */
+int dsep_sde_corrector_ald(const dsep_sde_params* p, const float* x, const float* score, const float* t,
+                           const float* noise, uint64_t seed, uint64_t offset, float snr, int B, int T,
+                           float* x_out, float* x_mean, dsep_stream_t stream);
+/* langevin (sdes/correctors.py:35-55): step = 2 (snr mean_b||z_b|| / mean_b||score_b||)^2 (batch means
+ * of per-entry L2 norms); xm = x + step score ; x' = xm + sqrt(2 step) z.  x, score, noise: [B, n];
+ * norms: float scratch [2, B].  noise is an explicit tensor (dsep_randn). */
+int dsep_sde_corrector_langevin(const float* x, const float* score, const float* noise, float snr, int B,
+                                int n, float* norms, float* x_out, float* x_mean, dsep_stream_t stream);
 /* PriorMixSDE._std_sigma_mix (sdes/sdes.py:477-489): 0.5 sqrt(clamp(avgpool_k(mix^2), 1e-4)). */
 int dsep_sigma_mix(const float* mix, int B, int T, int avg_len, float* sigma, dsep_stream_t stream);
 /* normalize_batch (pl_model.py:81-88): per-utterance (x - mean) / clamp(std_unbiased, 1e-5). */

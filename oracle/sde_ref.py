@@ -109,6 +109,53 @@ def corrector_step(p, score_fn, x, t, mix, noises, snr):
     return x, x_mean
 
 
+def ald_step(p, score_fn, x, t, mix, noises, snr):
+    """ald: correctors.py:58-91 (MixSDE only).  std = sqrt(first-row sum of L L) = sqrt(ev1)."""
+    ev1, _ = cov_eigval(p, t)
+    std = ev1.sqrt()[:, None, None]
+    x_mean = x
+    for nz in noises:
+        grad = score_fn(x, t, mix)
+        step = (snr * std) ** 2 * 2
+        x_mean = x + step * grad
+        x = x_mean + nz * torch.sqrt(step * 2)
+    return x, x_mean
+
+
+def langevin_step(p, score_fn, x, t, mix, noises, snr):
+    """langevin: correctors.py:35-55 (batch-mean norms couple the batch entries)."""
+    x_mean = x
+    for nz in noises:
+        grad = score_fn(x, t, mix)
+        grad_norm = torch.norm(grad.reshape(grad.shape[0], -1), dim=-1).mean()
+        noise_norm = torch.norm(nz.reshape(nz.shape[0], -1), dim=-1).mean()
+        step = (snr * noise_norm / grad_norm) ** 2 * 2
+        x_mean = x + step * grad
+        x = x_mean + nz * torch.sqrt(step * 2)
+    return x, x_mean
+
+
+def pc_sampler_plugins(p, score_fn, mix, noises, predictor="reverse_diffusion", corrector="ald2", eps=0.03, snr=0.5,
+                       corrector_steps=1, denoise=True):
+    """sdes/__init__.py:166-190 over the other registered plugins.  ``euler_maruyama``
+    is algebraically ``reverse_diffusion``; ``probability_flow`` has no effect in the reference (the
+    flag never reaches ``reverse()``, predictors.py:13-18), so it is not a parameter here."""
+    noises = list(noises)
+    xt = prior_sampling(p, mix, noises.pop(0))
+    ts = timesteps(p, eps, None, mix.dtype)
+    corr = {"ald2": corrector_step, "ald": ald_step, "langevin": langevin_step}[corrector]
+    xt_mean = xt
+    for i in range(p.N):
+        vec_t = torch.ones(mix.shape[0], dtype=mix.dtype) * ts[i]
+        cn = [noises.pop(0) for _ in range(corrector_steps)]
+        xt, xt_mean = corr(p, score_fn, xt, vec_t, mix, cn, snr)
+        if predictor == "none":
+            xt_mean = xt
+        else:
+            xt, xt_mean = predictor_step(p, score_fn, xt, vec_t, mix, noises.pop(0))
+    return xt_mean if denoise else xt
+
+
 def timesteps(p, eps, schedule=None, dtype=torch.float32):
     """sdes/__init__.py:175 (plain) and :92-111 (scheduled; N+1 points, dt unchanged)."""
     if schedule is None:

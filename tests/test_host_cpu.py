@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS)
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_abi_argument_counts_match_header():
@@ -77,7 +77,7 @@ def test_synthetic_weights_match_oracle_copy():
 def test_registries_and_errors():
     from diffsep_b200 import sdes
     assert set(sdes.PredictorRegistry.get_all_names()) == {"euler_maruyama", "reverse_diffusion", "none"}
-    assert set(sdes.CorrectorRegistry.get_all_names()) == {"ald2", "none"}
+    assert set(sdes.CorrectorRegistry.get_all_names()) == {"ald2", "ald", "langevin", "none"}
     assert set(sdes.SDERegistry.get_all_names()) == {"mix", "priormix"}
     with pytest.raises(ValueError, match="unknown"):
         sdes.PredictorRegistry.get_by_name("heun")

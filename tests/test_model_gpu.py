@@ -420,3 +420,52 @@ def test_evaluate_batch_driver(tmp_path):
         for s in (0, 1):
             sr_, data = wavfile.read(tmp_path / "out" / f"s{s}" / f"u{i}.wav")
             assert sr_ == 8000 and data.shape == (n,) and np.isfinite(data).all()
+
+
+@pytest.mark.parametrize("case", [("em_ald2", "euler_maruyama", "ald2", "mix", 1, False),
+                                  ("rd_ald", "reverse_diffusion", "ald", "mix", 2, False),
+                                  ("rd_langevin", "reverse_diffusion", "langevin", "mix", 1, False),
+                                  ("rd_langevin_prior", "reverse_diffusion", "langevin", "priormix", 1, False),
+                                  ("rd_ald2_pflow", "reverse_diffusion", "ald2", "mix", 1, True),
+                                  ("em_ald2_pflow", "euler_maruyama", "ald2", "priormix", 1, True),
+                                  ("none_ald2", "none", "ald2", "mix", 1, False)], ids=lambda c: c[0])
+def test_sampler_other_plugins_match_reference_golden(golden, case):
+    """The remaining registered plugins against the real reference sampler."""
+    from diffsep_b200 import sdes
+    from diffsep_b200.pl_model import normalize_batch
+    name, pred, corr, sde_name, cs, pflow = case
+    g = golden("plugins.npz")
+    (mix, _), _, _ = normalize_batch((cases.batch_mix(2, 1024).to(DEV), None))
+    sde = sdes.SDERegistry.get_by_name(sde_name)(ndim=2, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5, N=10)
+    with sdes.injected_noise(cases.sampler_noises(2, 1024, 10, cs)):
+        out, nfe = sdes.get_pc_sampler(pred, corr, sde=sde, score_fn=cases.analytic_score, y=mix, eps=0.03, snr=0.5,
+                                       corrector_steps=cs, denoise=False, probability_flow=pflow)()
+    torch.cuda.synchronize()
+    assert nfe == 10 * (cs + 1)
+    assert rel_l2(out.cpu(), g[name]) < 1e-5
+
+
+def test_ald_rejects_priormix_like_the_reference():
+    from diffsep_b200 import sdes
+    sde = sdes.PriorMixSDE(2, 2.0, 0.05, 0.5, N=3)
+    with pytest.raises(NotImplementedError):
+        sdes.get_pc_sampler("reverse_diffusion", "ald", sde=sde, score_fn=cases.analytic_score,
+                            y=torch.zeros(1, 1, 64, device=DEV))
+
+
+def test_probability_flow_kernel_switch():
+    """dsep_sde_predictor(probability_flow=1): half the score term, no noise (sdes.py:143-152,167-170) —
+    reachable through sde.reverse(score_fn, probability_flow=True), not through the predictors."""
+    from diffsep_b200 import ops
+    from oracle import sde_ref as sd
+    B, T = 2, 512
+    g = cases.gen(14)
+    mix, x, score, z = (torch.randn(B, c, T, generator=g) for c in (1, 2, 2, 2))
+    t = torch.tensor([0.9, 0.2])
+    p = sd.MixSDEParams(N=10)
+    want_x, want_m = sd.predictor_step(p, lambda *_: 0.5 * score, x, t, mix, torch.zeros_like(z))
+    xo, xm = torch.empty(B, 2, T, device=DEV), torch.empty(B, 2, T, device=DEV)
+    ops.sde_predictor(ops.sde_params(2.0, 0.05, 0.5), x.to(DEV), score.to(DEV), t.to(DEV), None, z.to(DEV), 0, 0,
+                      0.1, B, T, xo, xm, probability_flow=True)
+    torch.cuda.synchronize()
+    assert rel_l2(xo.cpu(), want_x) < 2e-6 and rel_l2(xm.cpu(), want_m) < 2e-6

@@ -157,3 +157,23 @@ def test_score_model_nf128(golden):
     with torch.no_grad():
         y = sr.score_forward(params, xt, t, mix)
     assert rel_l2(y, g["y"]) < 1e-5
+
+
+PLUGIN_CASES = [("em_ald2", "euler_maruyama", "ald2", False, 1), ("rd_ald", "reverse_diffusion", "ald", False, 2),
+                ("rd_langevin", "reverse_diffusion", "langevin", False, 1),
+                ("rd_langevin_prior", "reverse_diffusion", "langevin", True, 1),
+                ("rd_ald2_pflow", "reverse_diffusion", "ald2", False, 1), ("em_ald2_pflow", "euler_maruyama", "ald2", True, 1),
+                ("none_ald2", "none", "ald2", False, 1)]
+
+
+@pytest.mark.parametrize("case", PLUGIN_CASES, ids=lambda c: c[0])
+def test_sampler_other_plugins(golden, case):
+    """ald / langevin correctors, euler_maruyama / none predictors, and the reference's no-op
+    probability_flow flag, vs the real reference sampler (tests/golden/make_golden_plugins.py)."""
+    name, pred, corr, prior, cs = case
+    g = golden("plugins.npz")
+    mix, _, _ = sd.normalize_batch(cases.batch_mix(2, 1024))
+    p = sd.MixSDEParams(N=10, prior=prior)
+    out = sd.pc_sampler_plugins(p, cases.analytic_score, mix, cases.sampler_noises(2, 1024, 10, cs), predictor=pred,
+                                corrector=corr, corrector_steps=cs, denoise=False)
+    assert rel_l2(out, g[name]) < 5e-6

@@ -1,1 +1,1 @@
-python -m pytest tests -q -m gpu 2>&1 | tail -5
+python -m pytest tests/test_model_gpu.py -q -k "other_plugins or ald_rejects or probability_flow or registry" 2>&1 | tail -5
