@@ -76,9 +76,14 @@ def load():
     if _lib is not None:
         return _lib
     if not LIB_PATH.exists():
-        raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m diffsep_b200.build` "
-            "(there is no CPU or PyTorch fallback for the DiffSep hot path)")
+        # a source checkout without the binary: compile it in-tree (nvcc, sm_100a).  This is still the
+        # CUDA path — there is no CPU or PyTorch fallback for the DiffSep hot path.
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:
+            raise RuntimeError(f"{LIB_PATH} is missing and could not be built "
+                               f"(`python -m diffsep_b200.build`): {e}") from e
     lib = C.CDLL(str(LIB_PATH))
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)
