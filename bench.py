@@ -310,17 +310,24 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
         run = lambda: ops.conv2d_tc(a, B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, bias=cw.bias, film=film,
                                     film_stride=Cc, acc_scale=cw.acc_scale, stats=stats, passes=passes)
         variant = "fp16 hi/lo operand planes by TMA, FiLM + GN statistics in the epilogue"
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    reps = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    def time_it(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = time_it(run)
+    # for reference: the same convolution fed with ready-made operand planes (no prologue, no statistics)
+    ap = ops.Split.empty((B, H, W, Cc), dev)
+    ops.split_f16(x, ap)
+    ms_planes = time_it(lambda: ops.conv2d_tc(ap, B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, bias=cw.bias,
+                                              acc_scale=cw.acc_scale, passes=passes))
     flops = 2.0 * B * H * W * 9 * Cc * Cc
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops", 1590.0)
@@ -333,6 +340,9 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "ms_per_launch": ms, "algorithmic_gflop_per_launch": flops / 1e9, "mma_passes": passes,
             "issued_frac": passes * achieved / peak, "traffic": traffic,
+            "bare_conv": {"ms_per_launch": ms_planes, "achieved": flops / (ms_planes * 1e-3) / 1e12,
+                          "frac": flops / (ms_planes * 1e-3) / 1e12 / peak,
+                          "note": "same conv with precomputed operand planes, no prologue / FiLM / statistics"},
             "algorithmic_bytes_per_launch": 2 * 4.0 * B * H * W * Cc}
 
 
