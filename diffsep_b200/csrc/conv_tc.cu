@@ -190,7 +190,12 @@ __device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bo
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float t = fmaf(y[e], k_sc[e], k_sh[e]);
-                if (act) t = __fdividef(t, 1.0f + __expf(-t));
+                if (act) {   // SiLU = t / (1 + 2^(-t log2 e)): ex2.approx.ftz + rcp.approx.ftz, no range fix-ups
+                    float ex, rc;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t * -1.4426950408889634f));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+                    t *= rc;
+                }
                 y[e] = t;
             }
         }
