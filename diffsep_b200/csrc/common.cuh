@@ -113,6 +113,35 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: TMA loads land in the issuing CTA's shared memory but complete on
+// the LEADER CTA's mbarrier (the even CTA of the pair: bit 24 of the shared::cluster address cleared)
+__device__ __forceinline__ uint32_t leader_bar(uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+
 // ---- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,6 +167,36 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_in_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst_in_smem)),
+                 "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)
+                 : "memory");
+}
+// CTA-pair MMA: M = 256 (128 rows from each CTA's A tile), B rows split between the two CTAs' smem,
+// accumulator rows in each CTA's own TMEM.  Issued by one thread of the leader CTA.
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
         : "memory");
 }
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.

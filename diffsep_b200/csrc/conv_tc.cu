@@ -208,7 +208,10 @@ __device__ __forceinline__ void build_patch(uint8_t* dst_hi, uint8_t* dst_lo, bo
     }
 }
 
-template <int NT, bool HALO>
+// TWO (halo mode only): the pair issues ONE tcgen05.mma.cta_group::2 per step from the leader CTA
+// (M = 256: 128 pixels from each CTA; the B rows are split between the two CTAs' shared memory), which
+// halves the B-operand shared-memory reads and ingest per SM — the resource the 1-CTA kernel saturates.
+template <int NT, bool HALO, bool TWO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -253,19 +256,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NS; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 2);    // one tcgen05.commit from each CTA of the pair
+            mbar_init(&empty[i], TWO ? 1 : 2);    // 1-CTA MMAs: one tcgen05.commit from each CTA of the pair
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], NT >= 64 ? kEpiWarps : 4);   // narrow tiles: only 4 warps drain TMEM
+            // narrow tiles: only 4 warps drain TMEM; TWO: the leader collects both CTAs' epilogue warps
+            mbar_init(&tempty[i], NT >= 64 ? (TWO ? 2 * kEpiWarps : kEpiWarps) : 4);
         }
         for (int i = 0; i < NA; ++i) {
-            mbar_init(&afull[i], 1);
+            mbar_init(&afull[i], (TWO && p.fx0 != nullptr) ? 2 : 1);   // TWO + built patches: one arrival per CTA
             mbar_init(&aempty[i], 1);
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_ptr);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // both CTAs' barriers are initialised before any multicast targets them
@@ -303,7 +310,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 // generic-proxy writes -> visible to the tensor core's async proxy, then publish
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, %0;" ::"n"(kBuilders) : "memory");
-                if (wtid == 0) mbar_arrive(&afull[as_]);
+                if (wtid == 0) {
+                    if (TWO && rank != 0) mbar_arrive_cluster(&afull[as_], 0);   // the leader's MMA thread waits
+                    else mbar_arrive(&afull[as_]);
+                }
                 if (++as_ == kHaloAStages) { as_ = 0; aph ^= 1u; }
             }
         }
@@ -319,15 +329,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 mbar_wait(&empty[bs], bph ^ 1u);
                 uint8_t* sb = stage_base + NA * HCfg::kAStage + bs * HCfg::kBStage;
                 if (p.debug & 2) {
-                    mbar_arrive(&full[bs]);
+                    if (!TWO || rank == 0) mbar_arrive(&full[bs]);
                     if (++bs == NS) { bs = 0; bph ^= 1u; }
                     return;
                 }
-                mbar_arrive_expect_tx(&full[bs], planes * HCfg::kBBytes);
-                const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);
-                const int boff = static_cast<int>(rank) * (HCfg::kBBytes / 2);
-                tma_load_2d_mc(sb + boff, whi, &full[bs], kcol, wrow_h, 0x3);
-                if (three) tma_load_2d_mc(sb + HCfg::kBBytes + boff, wlo, &full[bs], kcol, wrow_h, 0x3);
+                if constexpr (TWO) {
+                    // B rows are split between the CTAs.  X (NT rows): W_hi in the leader, W_lo in the
+                    // follower = the two halves of the stacked [W_hi ; W_lo]; Y (NT/2 rows): this CTA's
+                    // half of W_hi for the A_lo x W_hi product.  Everything completes on the leader's barrier.
+                    if (rank == 0)
+                        mbar_arrive_expect_tx(&full[bs], three ? 3u * HCfg::kBBytes : 1u * HCfg::kBBytes);
+                    if (three) {
+                        const CUtensorMap* wx = rank == 0 ? whi : wlo;
+                        tma_load_2d_2sm(sb, wx, &full[bs], kcol, wrow);
+                        tma_load_2d_2sm(sb + HCfg::kBBytes / 2, wx, &full[bs], kcol, wrow + NT / 2);
+                    }
+                    tma_load_2d_2sm(sb + HCfg::kBBytes, whi, &full[bs], kcol, wrow + static_cast<int>(rank) * (NT / 2));
+                } else {
+                    mbar_arrive_expect_tx(&full[bs], planes * HCfg::kBBytes);
+                    const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);
+                    const int boff = static_cast<int>(rank) * (HCfg::kBBytes / 2);
+                    tma_load_2d_mc(sb + boff, whi, &full[bs], kcol, wrow_h, 0x3);
+                    if (three) tma_load_2d_mc(sb + HCfg::kBBytes + boff, wlo, &full[bs], kcol, wrow_h, 0x3);
+                }
                 if (++bs == NS) { bs = 0; bph ^= 1u; }
             };
             for (int item = cluster_id; item < p.total_items; item += num_clusters) {
@@ -349,6 +373,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         uint8_t* sa = stage_base + as_ * HCfg::kAStage;
                         if (p.debug & 2) {
                             mbar_arrive(&afull[as_]);
+                        } else if constexpr (TWO) {
+                            if (rank == 0) mbar_arrive_expect_tx(&afull[as_], 2u * planes * 16384u);
+                            tma_load_4d_2sm(sa, &tm_a2_hi, &afull[as_], kb * 64, w0, h0, b0);
+                            if (three) tma_load_4d_2sm(sa + kPatchPlane, &tm_a2_lo, &afull[as_], kb * 64, w0, h0, b0);
                         } else {
                             mbar_arrive_expect_tx(&afull[as_], planes * 16384u);
                             tma_load_4d(sa, &tm_a2_hi, &afull[as_], kb * 64, w0, h0, b0);
@@ -364,6 +392,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         uint8_t* sa = stage_base + as_ * HCfg::kAStage;
                         if (p.debug & 2) {
                             mbar_arrive(&afull[as_]);
+                        } else if constexpr (TWO) {
+                            if (rank == 0) mbar_arrive_expect_tx(&afull[as_], 2u * planes * patch_bytes);
+                            tma_load_4d_2sm(sa, &tm_a_hi, &afull[as_], kb * 64, w0 - hal, h0 - hal, b0);
+                            if (three)
+                                tma_load_4d_2sm(sa + kPatchPlane, &tm_a_lo, &afull[as_], kb * 64, w0 - hal, h0 - hal, b0);
                         } else {
                             mbar_arrive_expect_tx(&afull[as_], planes * patch_bytes);
                             tma_load_4d(sa, &tm_a_hi, &afull[as_], kb * 64, w0 - hal, h0 - hal, b0);
@@ -377,11 +410,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && HALO) {
+    } else if (warp == 1 && lane == 0 && HALO && !(TWO && rank != 0)) {
         // ------------------------------------------------------------------ MMA issuer (halo mode)
         if constexpr (HALO) {
-            constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
-            constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
+            constexpr uint32_t idesc_n = umma_idesc_f16(TWO ? 256 : 128, NT);
+            constexpr uint32_t idesc_2n = umma_idesc_f16(TWO ? 256 : 128, 2 * NT);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_flag) {
+                if constexpr (TWO) umma_f16_2cta(d, a, b, idesc, acc_flag);
+                else umma_f16(d, a, b, idesc, acc_flag);
+            };
+            auto commit_pair = [&](uint64_t* bar) {      // arrive in BOTH CTAs when the MMAs so far retire
+                if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
+                else umma_commit_mc(bar, 0x3);
+            };
+            auto commit_local = [&](uint64_t* bar) {     // TWO: the follower's barriers need the arrival too
+                if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
+                else umma_commit(bar);
+            };
             int bs = 0, as_ = 0;
             uint32_t bph = 0, aph = 0;
             int it = 0;
@@ -401,23 +446,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         if (p.debug & 1) break;
                         const uint64_t a_hi = umma_desc_sw128_sbo(a_base + a_off + k * 32, sbo, (p.debug & 8) != 0);
                         const uint64_t b_hi = umma_desc_sw128(sb + k * 32);          // W_hi rows, then W_lo rows
+                        // TWO: region X (this CTA's half of [W_hi ; W_lo]) / region Y (its half of W_hi)
+                        const uint64_t b_y = TWO ? umma_desc_sw128(sb + HCfg::kBBytes + k * 32) : b_hi;
                         if (three) {
-                            umma_f16(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
+                            mma(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
                             const uint64_t a_lo = umma_desc_sw128_sbo(a_base + kPatchPlane + a_off + k * 32, sbo, (p.debug & 8) != 0);
-                            umma_f16(d_tmem, a_lo, b_hi, idesc_n, 1);
+                            mma(d_tmem, a_lo, b_y, idesc_n, 1);
                         } else {
-                            umma_f16(d_tmem, a_hi, b_hi, idesc_n, accumulate);
+                            mma(d_tmem, a_hi, b_y, idesc_n, accumulate);
                         }
                         accumulate = 1;
                     }
-                    umma_commit_mc(&empty[bs], 0x3);
+                    commit_pair(&empty[bs]);
                     if (++bs == NS) { bs = 0; bph ^= 1u; }
                 };
                 for (int kb = 0; kb < p.kblocks2; ++kb) {      // fused 1x1 shortcut K-blocks
                     mbar_wait(&afull[as_], aph);
                     tc_fence_after();
                     issue(smem_u32(stage_base + as_ * HCfg::kAStage), 0u, 1024u);
-                    umma_commit(&aempty[as_]);
+                    commit_local(&aempty[as_]);
                     if (++as_ == NA) { as_ = 0; aph ^= 1u; }
                 }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -430,13 +477,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     } else {
                         issue(sa, 0u, 1024u);
                     }
-                    umma_commit(&aempty[as_]);
+                    commit_local(&aempty[as_]);
                     if (++as_ == NA) { as_ = 0; aph ^= 1u; }
                 }
-                umma_commit(&tfull[acc]);
+                commit_local(&tfull[acc]);
             }
         }
-    } else if (warp == 0 && lane == 0) {
+    } else if (!HALO && warp == 0 && lane == 0) {
         // ------------------------------------------------------------------ TMA producer (per-tap mode)
         int stage = 0;
         uint32_t phase = 0;
@@ -482,7 +529,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (!HALO && warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
         constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
@@ -643,7 +690,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     if (c == kChunks - 1) {   // TMEM fully drained by this warp: hand the buffer back early
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[as]);
+                        if (lane == 0) {
+                            if (TWO && rank != 0) mbar_arrive_cluster(&tempty[as], 0);   // the leader issues the MMAs
+                            else mbar_arrive(&tempty[as]);
+                        }
                     }
                     // transpose through smem: row = lane, 16-byte chunk j stored at j ^ (lane & 7)
                     float4* dst = reinterpret_cast<float4*>(stg + lane * 32);
@@ -764,7 +814,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // the peer may still multicast into / arrive on this CTA's shared memory
-    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -820,13 +873,13 @@ struct ConvMaps {
     CUtensorMap a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, w2_hi, w2_lo;
 };
 
-template <int NT, bool HALO>
+template <int NT, bool HALO, bool TWO = false>
 static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
     constexpr int kSmem = HALO ? HaloCfg<NT>::kSmemBytes : ConvCfg<NT>::kSmemBytes;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_tc_kernel<NT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        attr_err = cudaFuncSetAttribute(conv_tc_kernel<NT, HALO, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     });
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>): %s", NT, (int)HALO, cudaGetErrorString(attr_err));
@@ -834,7 +887,7 @@ static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stre
     }
     const int max_clusters = num_sms() / 2;
     const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
-    conv_tc_kernel<NT, HALO><<<grid, kThreads, kSmem, stream>>>(
+    conv_tc_kernel<NT, HALO, TWO><<<grid, kThreads, kSmem, stream>>>(
         m.a_hi, m.a_lo, m.w_hi, m.w_lo, m.a2_hi, m.a2_lo, m.w2_hi, m.w2_lo, p);
     return check_launch("conv_tc_kernel");
 }
@@ -973,6 +1026,9 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
         }
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
+    if (halo && two_env)
+        return NT == 64 ? launch_conv<64, true, true>(m, p, s) : launch_conv<128, true, true>(m, p, s);
     if (halo) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);
     switch (NT) {
         case 16: return launch_conv<16, false>(m, p, s);

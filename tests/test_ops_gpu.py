@@ -469,3 +469,15 @@ def test_normalize_and_scale_output(golden):
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), g["norm"]) < 1e-6
     assert rel_l2(sc.cpu(), g["scaled"]) < 1e-6
+
+
+def test_conv_variants_cta_pair_mma_and_per_tap():
+    """The optional kernel variants — DSEP_CONV_2CTA=1 (one tcgen05.mma.cta_group::2 per CTA pair) and
+    DSEP_CONV_HALO=0 (per-tap TMA boxes) — pass the same conv parity tests (switches are read once per
+    process, hence the subprocesses)."""
+    import os, subprocess, sys
+    for env in ({"DSEP_CONV_2CTA": "1"}, {"DSEP_CONV_HALO": "0"}):
+        r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k",
+                            "test_conv2d_tc and not variants"], env=dict(os.environ, **env), capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, (env, r.stdout[-2000:])
