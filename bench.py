@@ -163,7 +163,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch.distributed as dist
-    from diffsep_b200 import _lib, ops, sdes
+    from diffsep_b200 import _lib, ops
     from diffsep_b200.pl_model import DEFAULT_CONFIG, DiffSepModel
     from diffsep_b200 import synthetic as ow
 

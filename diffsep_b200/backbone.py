@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import math
 import os
-from collections import OrderedDict
 
 import torch
 

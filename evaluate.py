@@ -38,7 +38,6 @@ def summarize(results):
 
 def main(argv=None):
     import separate as sep_cli
-    from diffsep_b200 import ops
     from diffsep_b200.data import load_wav, max_collator, save_wav, uncollate
     from diffsep_b200.shard import shard_bounds
     import torch.distributed as dist
