@@ -259,6 +259,11 @@ class NCSNppB200:
             self._plans[key] = _Plan(self, B, W)
         return self._plans[key]
 
+    def drop_plan(self, B, W, keep=()):
+        """forget the launch plan (and its arena) of a shape no caller uses any more"""
+        if (B, W) not in keep:
+            self._plans.pop((B, W), None)
+
     def __call__(self, x_planes: Split, x_pyramid, t):
         """x_planes: split [B,256,W,conv_in.cin_pad] network input (2x-1 applied, channels >= ch_in zero);
         x_pyramid: the same input as fp32 [B,256,W,ch_in]; t: [B].  Returns the output pyramid

@@ -112,10 +112,19 @@ class ScoreModelNCSNpp(torch.nn.Module):
         return self
 
     # -------------------------------------------------------------- buffers per (B, T)
+    MAX_SHAPES = 4   # distinct (batch, length) shapes kept resident (buffers, launch plan, CUDA graph)
+
     def _work(self, B, T):
         key = (B, T)
         if key in self._bufs:
+            self._bufs[key] = self._bufs.pop(key)        # most recently used last
             return self._bufs[key]
+        while len(self._bufs) >= self.MAX_SHAPES:        # ragged evaluation sets: do not hoard old shapes
+            old = next(iter(self._bufs))
+            del self._bufs[old]
+            if self.backbone is not None:
+                self.backbone.drop_plan(old[0], (n_frames(old[1]) + 63) // 64 * 64,
+                                        keep={(b, (n_frames(t) + 63) // 64 * 64) for b, t in self._bufs})
         dev, ns = self.dev, self.num_sources
         Fr = n_frames(T)
         Wp = (Fr + 63) // 64 * 64

@@ -506,3 +506,13 @@ def test_per_step_parity_benchmark_architecture():
                 g, _ = sde.predictor_update(xc.to(DEV), model(xc.to(DEV), vt_d, mix), vt_d, mix, 1.0 / N)
             assert rel_l2(g.cpu(), xp) < 1e-4
             x = xp
+
+
+def test_shape_cache_is_bounded():
+    """ragged inputs: buffers / plans / graphs of at most MAX_SHAPES (B, T) shapes stay resident"""
+    sm = _score_model(64)
+    for T in (1000, 1500, 2000, 2500, 3000, 9000, 1000):
+        xt, t, mix = (v.to(DEV) for v in cases.score_inputs(1, T, seed=T))
+        y = sm(xt, t, mix)
+        assert y.shape == (1, 2, T) and bool(torch.isfinite(y).all())
+    assert len(sm._bufs) <= sm.MAX_SHAPES and len(sm.backbone._plans) <= sm.MAX_SHAPES
