@@ -239,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     uint64_t* aempty = afull + NA;     // [NA]   MMA -> TMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty + NA);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler too
     const int lane = threadIdx.x & 31;
     const bool three = p.passes == 3;
     // CTA pair: the two CTAs of a cluster work on M-adjacent tiles of the same channel tile, each
@@ -410,77 +410,103 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && HALO && !(TWO && rank != 0)) {
+    } else if (warp == 1 && HALO) {
         // ------------------------------------------------------------------ MMA issuer (halo mode)
+        // The WHOLE warp walks the pipeline in convergent control flow and one elected lane issues, so
+        // that barrier addresses, descriptors and the accumulate flag stay in uniform registers: a
+        // single-thread issuer spent ~20 vector instructions (elect / R2UR / vote loops) per
+        // tcgen05.mma and capped the tensor pipe at 68 % active (ncu, round 1).  Descriptors are
+        // (address >> 4) words advanced by immediates; the high word is a constant.
         if constexpr (HALO) {
-            constexpr uint32_t idesc_n = umma_idesc_f16(TWO ? 256 : 128, NT);
-            constexpr uint32_t idesc_2n = umma_idesc_f16(TWO ? 256 : 128, 2 * NT);
-            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_flag) {
-                if constexpr (TWO) umma_f16_2cta(d, a, b, idesc, acc_flag);
-                else umma_f16(d, a, b, idesc, acc_flag);
-            };
-            auto commit_pair = [&](uint64_t* bar) {      // arrive in BOTH CTAs when the MMAs so far retire
-                if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
-                else umma_commit_mc(bar, 0x3);
-            };
-            auto commit_local = [&](uint64_t* bar) {     // TWO: the follower's barriers need the arrival too
-                if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
-                else umma_commit(bar);
-            };
-            int bs = 0, as_ = 0;
-            uint32_t bph = 0, aph = 0;
-            int it = 0;
-            for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
-                const int acc = it & 1;
-                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * 2 * NT;
-                uint32_t accumulate = 0;
-                // one weight stage against the A rows starting at byte offset a_off, groups sbo bytes apart
-                auto issue = [&](uint32_t a_base, uint32_t a_off, uint32_t sbo) {
-                    mbar_wait(&full[bs], bph);
-                    tc_fence_after();
-                    const uint32_t sb = smem_u32(stage_base + NA * HCfg::kAStage + bs * HCfg::kBStage);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (p.debug & 1) break;
-                        const uint64_t a_hi = umma_desc_sw128_sbo(a_base + a_off + k * 32, sbo, (p.debug & 8) != 0);
-                        const uint64_t b_hi = umma_desc_sw128(sb + k * 32);          // W_hi rows, then W_lo rows
-                        // TWO: region X (this CTA's half of [W_hi ; W_lo]) / region Y (its half of W_hi)
-                        const uint64_t b_y = TWO ? umma_desc_sw128(sb + HCfg::kBBytes + k * 32) : b_hi;
-                        if (three) {
-                            mma(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
-                            const uint64_t a_lo = umma_desc_sw128_sbo(a_base + kPatchPlane + a_off + k * 32, sbo, (p.debug & 8) != 0);
-                            mma(d_tmem, a_lo, b_y, idesc_n, 1);
-                        } else {
-                            mma(d_tmem, a_hi, b_y, idesc_n, accumulate);
-                        }
-                        accumulate = 1;
-                    }
-                    commit_pair(&empty[bs]);
-                    if (++bs == NS) { bs = 0; bph ^= 1u; }
+            if (!(TWO && rank != 0)) {
+                const bool leader = elect_one();
+                constexpr uint32_t idesc_n = umma_idesc_f16(TWO ? 256 : 128, NT);
+                constexpr uint32_t idesc_2n = umma_idesc_f16(TWO ? 256 : 128, 2 * NT);
+                // high descriptor word: SBO >> 4 | version 1 (bit 46) | SWIZZLE_128B (bits 61-63)
+                constexpr uint32_t kHiPatch = ((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29);
+                constexpr uint32_t kHiPlain = (1024u >> 4) | (1u << 14) | (2u << 29);
+                auto desc = [](uint32_t lo, uint32_t hi) {
+                    uint64_t d;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+                    return d;
                 };
-                for (int kb = 0; kb < p.kblocks2; ++kb) {      // fused 1x1 shortcut K-blocks
-                    mbar_wait(&afull[as_], aph);
+                auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_flag) {
+                    if constexpr (TWO) umma_f16_2cta(d, a, b, idesc, acc_flag);
+                    else umma_f16(d, a, b, idesc, acc_flag);
+                };
+                auto commit_pair = [&](uint64_t* bar) {      // arrive in BOTH CTAs when the MMAs so far retire
+                    if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
+                    else umma_commit_mc(bar, 0x3);
+                };
+                auto commit_local = [&](uint64_t* bar) {     // TWO: the follower's barriers need the arrival too
+                    if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
+                    else umma_commit(bar);
+                };
+                const uint32_t a_ring = smem_u32(stage_base) >> 4;
+                const uint32_t b_ring = smem_u32(stage_base + NA * HCfg::kAStage) >> 4;
+                const bool do_mma = !(p.debug & 1);
+                int bs = 0, as_ = 0;
+                uint32_t bph = 0, aph = 0;
+                int it = 0;
+                for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
                     tc_fence_after();
-                    issue(smem_u32(stage_base + as_ * HCfg::kAStage), 0u, 1024u);
-                    commit_local(&aempty[as_]);
-                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
-                }
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&afull[as_], aph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(stage_base + as_ * HCfg::kAStage);
-                    if (p.taps == 9) {
-                        for (int tap = 0; tap < 9; ++tap)
-                            issue(sa, static_cast<uint32_t>(((tap / 3) * kPatchW + tap % 3) * 128), kPatchW * 128);
-                    } else {
-                        issue(sa, 0u, 1024u);
+                    const uint32_t d_tmem = tmem_base + acc * 2 * NT;
+                    uint32_t accumulate = 0;
+                    // one weight stage against the A rows whose hi-plane descriptor word is a_word
+                    auto issue = [&](uint32_t a_word, uint32_t a_hiword) {
+                        mbar_wait(&full[bs], bph);
+                        tc_fence_after();
+                        const uint32_t b_word = b_ring + bs * (HCfg::kBStage >> 4);   // W_hi rows, then W_lo rows
+                        if (leader) {
+                            if (do_mma) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t a_hi = desc(a_word + 2 * k, a_hiword);
+                                    const uint64_t b_hi = desc(b_word + 2 * k, kHiPlain);
+                                    // TWO: region X (this CTA's half of [W_hi ; W_lo]) / region Y (its half of W_hi)
+                                    const uint64_t b_y = TWO ? desc(b_word + (HCfg::kBBytes >> 4) + 2 * k, kHiPlain) : b_hi;
+                                    if (three) {
+                                        mma(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
+                                        mma(d_tmem, desc(a_word + (kPatchPlane >> 4) + 2 * k, a_hiword), b_y, idesc_n, 1);
+                                    } else {
+                                        mma(d_tmem, a_hi, b_y, idesc_n, accumulate);
+                                    }
+                                    accumulate = 1;
+                                }
+                            }
+                            commit_pair(&empty[bs]);
+                        }
+                        __syncwarp();
+                        if (++bs == NS) { bs = 0; bph ^= 1u; }
+                    };
+                    for (int kb = 0; kb < p.kblocks2; ++kb) {      // fused 1x1 shortcut K-blocks
+                        mbar_wait(&afull[as_], aph);
+                        tc_fence_after();
+                        issue(a_ring + as_ * (HCfg::kAStage >> 4), kHiPlain);
+                        if (leader) commit_local(&aempty[as_]);
+                        __syncwarp();
+                        if (++as_ == NA) { as_ = 0; aph ^= 1u; }
                     }
-                    commit_local(&aempty[as_]);
-                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&afull[as_], aph);
+                        tc_fence_after();
+                        const uint32_t sa = a_ring + as_ * (HCfg::kAStage >> 4);
+                        if (p.taps == 9) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap)
+                                issue(sa + ((tap / 3) * kPatchW + tap % 3) * 8, kHiPatch);
+                        } else {
+                            issue(sa, kHiPlain);
+                        }
+                        if (leader) commit_local(&aempty[as_]);
+                        __syncwarp();
+                        if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                    }
+                    if (leader) commit_local(&tfull[acc]);
+                    __syncwarp();
                 }
-                commit_local(&tfull[acc]);
             }
         }
     } else if (!HALO && warp == 0 && lane == 0) {
