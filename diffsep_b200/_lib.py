@@ -8,9 +8,11 @@ There is no fallback: if the library is missing or a call fails, the caller gets
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libdsep.so"
+# DSEP_LIB: load another build of the same sources (kernel experiments, tools/build_variant.sh)
+LIB_PATH = Path(os.environ.get("DSEP_LIB") or Path(__file__).resolve().parent / "libdsep.so")
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
 ABI_VERSION = 4
