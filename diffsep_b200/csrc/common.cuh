@@ -61,10 +61,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
             : "memory");
         if (done) return;
     }
