@@ -239,24 +239,9 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 
-// K-major, 128-byte-swizzled shared-memory operand descriptor (8-row x 128 B atoms, 1024 B apart).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);   // start address, 16 B units
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride between 8-row groups
-    d |= 1ull << 46;                                         // descriptor version (sm_100)
-    d |= 2ull << 61;                                         // SWIZZLE_128B
-    return d;
-}
-// Same for 64-byte-swizzled operands (32 fp16 of K per row; 8-row x 64 B atoms, 512 B apart).
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>(512 >> 4) << 32;
-    d |= 1ull << 46;
-    d |= 4ull << 61;                                         // SWIZZLE_64B
-    return d;
-}
+// Shared-memory operand descriptors (K-major, SWIZZLE_128B / SWIZZLE_64B) are assembled in conv_tc.cu from
+// an (address >> 4) low word advanced by immediates and a constant high word (stride between 8-row groups >> 4,
+// descriptor version 1 at bit 46, swizzle mode at bits 61-63), so that they stay in uniform registers.
 // Instruction descriptor (kind::f16): fp16 x fp16 -> fp32 (c_format = 1 at bit 4, a/b_format = 0
 // at bits 7/10), both operands K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {

@@ -24,10 +24,13 @@
 //     for the reference by default on a GPU);
 //   * the 1x1 shortcut convolution is extra K-blocks from a second operand (A2, W2) accumulated
 //     into the same TMEM tile: its output is never written to or re-read from HBM;
-//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer,
-//     warp 2 TMEM allocator, warps 4-11 epilogue (two warps per TMEM lane quarter, splitting
-//     the columns); smem ring of K-blocks with mbarrier full/empty pairs; the TMEM accumulator
-//     is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (the
+//     whole warp runs convergently so descriptors live in uniform registers; one elected lane
+//     issues), warp 2 TMEM allocator, warps 4-11 workers: patch builders + epilogue (two warps per
+//     TMEM lane quarter, splitting the columns).  Halo kernels move registers from the control
+//     warpgroup to the worker warpgroups with setmaxnreg (56 / 224).  smem ring of K-blocks with
+//     mbarrier full/empty pairs; the TMEM accumulator is double-buffered so the epilogue of tile i
+//     overlaps the MMAs of tile i+1;
 //   * epilogue: residual prefetched into registers, tcgen05.ld -> XOR-swizzled per-warp smem
 //     transpose (conflict-free both ways) -> bias/FiLM/residual/scale fused -> 128-byte
 //     coalesced fp32 stores; per-channel (sum, sum^2) reduced in registers + 2 shuffles and
@@ -96,9 +99,6 @@ struct ConvCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 512 + 1024;
 };
 
-__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
-    return kBK == 64 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
-}
 
 // ---- "halo" mode (3x3, maps of at least 16 x 8): the A operand of all nine taps comes from ONE
 // shared-memory patch.  The output tile is 8 (w) x 16 (h) pixels; its 10 x 18 input patch of 64
@@ -125,19 +125,10 @@ struct HaloCfg {
     static constexpr int kSmemBytes = kHaloAStages * kAStage + kBStages * kBStage + kStagingBytes + 512 + 1024;
 };
 
-__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes, bool base_off) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
-    d |= 1ull << 46;
-    if (base_off) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;   // swizzle phase of the start row
-    d |= 2ull << 61;
-    return d;
-}
 
 // Builds one 64-channel A patch (PH x PW pixels, row = py * PW + px, 128-byte-swizzled K-major rows of
 // (hi, lo) fp16) from fp32 activations: y = act(x * sc[c] + sh[c]), zero outside the image (the conv
-// pads the ACTIVATED tensor).  Called by the kBuilders builder threads; wtid = 0..319.  Replaces the
+// pads the ACTIVATED tensor).  Called by the kBuilders builder threads; wtid = 0..255.  Replaces the
 // GroupNorm-apply + SiLU + split pass (and the channel concat) that used to run as its own kernel.
 constexpr int kBuilders = 256;   // the 8 worker warps (two warpgroups, 224 registers each after setmaxnreg)
 
@@ -633,10 +624,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (!HALO && warp == 1 && lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (!HALO && warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (per-tap mode)
+        // whole warp, convergent, one elected lane issues: descriptors stay in uniform registers (see halo mode)
+        const bool leader = elect_one();
         constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
         constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
+        constexpr uint32_t kHi = kBK == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
+        auto desc = [](uint32_t lo, uint32_t hi) {
+            uint64_t d;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+            return d;
+        };
+        const uint32_t ring = smem_u32(stage_base) >> 4;
+        const bool do_mma = !(p.debug & 1);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -645,27 +646,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * 2 * NT;
+            uint32_t accumulate = 0;
             for (int ki = 0; ki < kiters; ++ki) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t s = smem_u32(stage_base + stage * Cfg::kStageBytes);
+                const uint32_t s = ring + stage * (Cfg::kStageBytes >> 4);
+                if (leader) {
+                    if (do_mma) {
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    if (p.debug & 1) break;
-                    const uint64_t a_hi = umma_desc_k(s + k * 32);
-                    const uint64_t b_hi = umma_desc_k(s + 2 * kABytes + k * 32);   // W_hi rows, then W_lo rows
-                    if (three) {
-                        umma_f16(d_tmem, a_hi, b_hi, idesc_2n, (ki | k) != 0);
-                        const uint64_t a_lo = umma_desc_k(s + kABytes + k * 32);
-                        umma_f16(d_tmem, a_lo, b_hi, idesc_n, 1);
-                    } else {
-                        umma_f16(d_tmem, a_hi, b_hi, idesc_n, (ki | k) != 0);
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            const uint64_t a_hi = desc(s + 2 * k, kHi);
+                            const uint64_t b_hi = desc(s + ((2 * kABytes) >> 4) + 2 * k, kHi);   // W_hi rows, then W_lo rows
+                            if (three) {
+                                umma_f16(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
+                                umma_f16(d_tmem, desc(s + (kABytes >> 4) + 2 * k, kHi), b_hi, idesc_n, 1);
+                            } else {
+                                umma_f16(d_tmem, a_hi, b_hi, idesc_n, accumulate);
+                            }
+                            accumulate = 1;
+                        }
                     }
+                    umma_commit_mc(&empty[stage], 0x3);   // frees this slot in BOTH CTAs once these MMAs retire
                 }
-                umma_commit_mc(&empty[stage], 0x3);   // frees this slot in BOTH CTAs once these MMAs retire
+                __syncwarp();
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(&tfull[as]);          // accumulator complete -> epilogue
+            if (leader) umma_commit(&tfull[as]);          // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue

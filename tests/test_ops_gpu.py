@@ -189,6 +189,53 @@ def test_conv2d_fused_prologue(shape, passes):
     assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 24, 128, 128), (1, 24, 20, 64, 128), (3, 16, 8, 128, 64), (1, 40, 36, 192, 256)])
+def test_conv2d_fused_film_residual_and_partial_tiles(shape):
+    """The ResBlock's two fused launches at op level: conv3x3(SiLU(GN(x))) + bias + FiLM[b] (Conv_0 + Dense_0) and
+    (conv3x3(SiLU(GN(h))) + bias + residual) / sqrt(2) (Conv_1 + skip), with the next GroupNorm's statistics, on
+    maps whose 8 x 16 tiles are whole (the epilogue's fast path) and on maps where they hang over the border
+    (24 x 20, 40 x 36: per-row predicates), vs float64."""
+    ops = _ops()
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, Cin, Cout = shape
+    g = cases.gen(sum(shape) + 7)
+    x = torch.randn(B, Cin, H, W, generator=g) * 0.9 + 0.1
+    gamma = 1 + 0.1 * torch.randn(Cin, generator=g)
+    beta = 0.1 * torch.randn(Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    film = torch.randn(B, Cout + 8, generator=g) * 0.3          # strided FiLM table, like the [N, 49, C] one
+    res = torch.randn(B, Cout, H, W, generator=g)
+    a_ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    a_ref = a_ref * torch.sigmoid(a_ref)
+    conv = F.conv2d(a_ref, w.double(), b1.double(), padding=1)
+    cw = ConvWeight(w, b1, DEV)
+    d0 = cl(x)
+    st0 = torch.empty(B, Cin, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, Cin, B, H * W, st0)
+    sc = torch.empty(B, Cin, device=DEV)
+    sh = torch.empty(B, Cin, device=DEV)
+    ops.gn_tables(st0, Cin, None, 0, B, H * W, 32, gamma.to(DEV), beta.to(DEV), 1e-6, sc, sh)
+    film_d = film.to(DEV)
+    for mode in ("film", "residual"):
+        out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+        stats = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+        if mode == "film":
+            ref = conv + film[:, :Cout].double()[:, :, None, None]
+            ops.conv2d_fused(B, H, W, Cin, cw.planes, cw.cout_pad, 3, out, Cout, x0=d0, C0=Cin, sc=sc, sh=sh, act=1,
+                             bias=cw.bias, film=film_d, film_stride=Cout + 8, acc_scale=cw.acc_scale, stats=stats)
+        else:
+            ref = (conv + res.double()) / math.sqrt(2.0)
+            ops.conv2d_fused(B, H, W, Cin, cw.planes, cw.cout_pad, 3, out, Cout, x0=d0, C0=Cin, sc=sc, sh=sh, act=1,
+                             bias=cw.bias, residual=cl(res), scale=1 / math.sqrt(2.0), acc_scale=cw.acc_scale,
+                             stats=stats)
+        torch.cuda.synchronize()
+        assert rel_l2(nchw(out), ref) < 1e-5, mode
+        got = nchw(out).double()
+        assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6, mode
+        assert rel_l2(stats[..., 1].cpu(), (got * got).sum(dim=(2, 3))) < 1e-6, mode
+
+
 def test_conv2d_fused_rejects_small_maps():
     ops = _ops()
     w = ops.Split.zeros((9, 64, 64), DEV)
