@@ -545,10 +545,13 @@ class _Plan:
             # output pyramid: conv3x3(SiLU(GN(h))) (+ FIR-up of the running pyramid), ncsnpp.py:419-440
             g = gn_groups(h.C)
             st = self._ensure_stats(h)
-            a = ar.split(B, h.H, h.W, h.C)
             gam, bet = level["pyr_gn"]
-            self.steps.append(lambda t=h.t, c=h.C, P=h.H * h.W, g=g, st=st, gam=gam, bet=bet, a=a:
-                              ops.gn_act_split(t, c, st, None, 0, None, B, P, g, gam, bet, GN_EPS, 1, a=a))
+            pyr_fused = self._fusable(h.H, h.W, h.C)
+            a = None
+            if not pyr_fused:
+                a = ar.split(B, h.H, h.W, h.C)
+                self.steps.append(lambda t=h.t, c=h.C, P=h.H * h.W, g=g, st=st, gam=gam, bet=bet, a=a:
+                                  ops.gn_act_split(t, c, st, None, 0, None, B, P, g, gam, bet, GN_EPS, 1, a=a))
             new_pyr = ar.f32(B, h.H, h.W, ch_in)
             up = None
             if pyramid is not None:
@@ -556,8 +559,13 @@ class _Plan:
                 self.steps.append(lambda src=pyramid, Hs=h.H // 2, Ws=h.W // 2, up=up: ops.fir_resample(
                     src, B, Hs, Ws, ch_in, 1, y=up))
                 ar.release(pyramid)
-            self._conv(a, h.H, h.W, h.C, level["pyr_conv"], new_pyr, ch_in, residual=up)
-            ar.release(a)
+            if pyr_fused:     # GN + SiLU + split in the conv's own prologue (halo kernel, 16-column output tile)
+                sc, sh = self._tables(st, h.C, None, 0, h.H * h.W, gam, bet)
+                self._conv_fused(h.H, h.W, h.C, level["pyr_conv"], new_pyr, ch_in, h.t, h.C, None, 0, sc, sh, 1,
+                                 residual=up)
+            else:
+                self._conv(a, h.H, h.W, h.C, level["pyr_conv"], new_pyr, ch_in, residual=up)
+                ar.release(a)
             if up is not None:
                 ar.release(up)
             pyramid = new_pyr

@@ -1142,11 +1142,12 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
     int th = 1 << ilog2(H); if (th > 128 / tw) th = 128 / tw;
     // halo mode: maps of at least 16 x 8 and wide output tiles; fixed 8 (w) x 16 (h) tile
     static const int halo_env = getenv("DSEP_CONV_HALO") ? atoi(getenv("DSEP_CONV_HALO")) : 1;
-    const bool halo_ok = kBK == 64 && W >= 8 && H >= 16 && Cout_pad != 16;
+    // narrow outputs (Cout_pad = 16: the pyramid convs) take the halo kernel only with the in-kernel prologue
+    const bool halo_ok = kBK == 64 && W >= 8 && H >= 16 && (Cout_pad != 16 || (main_fused && Cin2 == 0));
     const bool halo = halo_ok && (main_fused || short_fused || (halo_env != 0 && ksize == 3));
     DSEP_REQUIRE(!(main_fused || short_fused) || halo_ok,
-                 "conv2d_fused: the in-kernel prologue needs a map of at least 16 x 8 and Cout >= 64 "
-                 "(got %dx%d, Cout_pad %d)", H, W, Cout_pad);
+                 "conv2d_fused: the in-kernel prologue needs a map of at least 16 x 8 (and no fused shortcut when "
+                 "Cout_pad is 16; got %dx%d, Cout_pad %d)", H, W, Cout_pad);
     // all A patches of a launch come from ONE agent (TMA producer or worker warps): two agents sharing the
     // patch ring could fall a whole mbarrier phase apart
     DSEP_REQUIRE(Cin2 == 0 || main_fused == short_fused,
@@ -1238,6 +1239,7 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
+    if (halo && NT == 16) return launch_conv<16, true>(m, p, s);
     if (halo && two_env)
         return NT == 64 ? launch_conv<64, true, true>(m, p, s) : launch_conv<128, true, true>(m, p, s);
     if (halo) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);

@@ -236,6 +236,39 @@ def test_conv2d_fused_film_residual_and_partial_tiles(shape):
         assert rel_l2(stats[..., 1].cpu(), (got * got).sum(dim=(2, 3))) < 1e-6, mode
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 24, 128), (1, 24, 20, 256), (3, 16, 8, 64)])
+def test_conv2d_fused_narrow_output(shape):
+    """The output-pyramid branch (ncsnpp.py:419-440): conv3x3(SiLU(GN(h))) with 6 output channels (16-column
+    tensor-core tile) + the FIR-upsampled running pyramid as residual, prologue in-kernel, vs float64."""
+    ops = _ops()
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, Cin = shape
+    Cout = 6
+    g = cases.gen(sum(shape) + 11)
+    x = torch.randn(B, Cin, H, W, generator=g) * 1.1 - 0.2
+    gamma = 1 + 0.1 * torch.randn(Cin, generator=g)
+    beta = 0.1 * torch.randn(Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(B, Cout, H, W, generator=g)
+    a_ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    a_ref = a_ref * torch.sigmoid(a_ref)
+    ref = F.conv2d(a_ref, w.double(), b1.double(), padding=1) + res.double()
+    cw = ConvWeight(w, b1, DEV)
+    assert cw.cout_pad == 16
+    d0 = cl(x)
+    st0 = torch.empty(B, Cin, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, Cin, B, H * W, st0)
+    sc = torch.empty(B, Cin, device=DEV)
+    sh = torch.empty(B, Cin, device=DEV)
+    ops.gn_tables(st0, Cin, None, 0, B, H * W, 32, gamma.to(DEV), beta.to(DEV), 1e-6, sc, sh)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    ops.conv2d_fused(B, H, W, Cin, cw.planes, cw.cout_pad, 3, out, Cout, x0=d0, C0=Cin, sc=sc, sh=sh, act=1,
+                     bias=cw.bias, residual=cl(res), acc_scale=cw.acc_scale)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(out), ref) < 1e-5
+
+
 def test_conv2d_fused_rejects_small_maps():
     ops = _ops()
     w = ops.Split.zeros((9, 64, 64), DEV)
