@@ -75,7 +75,8 @@ int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int 
  *                     (the convolution pads the ACTIVATED tensor).  Replaces nn.GroupNorm + nn.SiLU +
  *                     torch.cat in front of Conv_0 / Conv_1 / NIN_0..2 (layerspp.py:292-309, 76-82).
  *   shortcut operand: s0 != NULL  =>  A2 = the raw fp32 [s0 (S0 ch) | s1 (S1 ch)] (S0 + S1 == Cin2).
- * Needs a map of at least 16 x 8 pixels and Cout >= 64 (smaller maps: dsep_gn_act_split + dsep_conv2d_tc). */
+ * Needs a map of at least 16 x 8 pixels; Cout_pad = 16 (the output-pyramid convs) is accepted without a fused
+ * shortcut and without statistics (smaller maps: dsep_gn_act_split + dsep_conv2d_tc). */
 typedef struct {
     const void *a_hi, *a_lo;            /* split planes [B,H,W,Cin], or NULL with x0 set            */
     const float *x0, *x1;               /* fp32 activations [B,H,W,C0], [B,H,W,C1]                  */
