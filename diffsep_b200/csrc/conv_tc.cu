@@ -75,14 +75,6 @@ constexpr int kThreads = 128 + kEpiWarps * 32;
 #ifndef DSEP_CONV_BK
 #define DSEP_CONV_BK 64
 #endif
-// 1: issue a patch's global loads before waiting for its slot (measured slower: the registers held across the
-// wait spill)
-#ifndef DSEP_EPI_RES_LATE
-#define DSEP_EPI_RES_LATE 0
-#endif
-#ifndef DSEP_LOAD_BEFORE_WAIT
-#define DSEP_LOAD_BEFORE_WAIT 0
-#endif
 constexpr int kBK = DSEP_CONV_BK;
 static_assert(kBK == 32 || kBK == 64, "K-block must be 32 or 64 channels");
 constexpr int kABytes = 128 * kBK * 2;     // one A plane of a stage
@@ -349,9 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             for (int pi = 0; pi < total; ++pi) {
                 const bool second = pi < p.kblocks2;
                 const uint32_t sa = smem_u32(stage_base + as_ * HaloCfg<NT>::kAStage);
-#if !DSEP_LOAD_BEFORE_WAIT
                 mbar_wait(&aempty[as_], aph ^ 1u);
-#endif
                 if (second || p.taps != 9) {
                     PatchRegs<8, 16> R;
                     if (!skip) {
@@ -362,18 +352,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             patch_load<8, 16>(R, p.fx0, p.fC0, p.fx1, p.fC1, pi - p.kblocks2, p.fsc, p.fsh, b0, h0, w0,
                                               p.B, p.H, p.W, wtid);
                     }
-#if DSEP_LOAD_BEFORE_WAIT
-                    mbar_wait(&aempty[as_], aph ^ 1u);
-#endif
                     if (!skip) patch_store<8, 16>(R, sa, sa + kPatchPlane, three, !second && p.fsc != nullptr, p.fact);
                 } else {
                     PatchRegs<kPatchW, kPatchH> R;
                     if (!skip)
                         patch_load<kPatchW, kPatchH>(R, p.fx0, p.fC0, p.fx1, p.fC1, pi - p.kblocks2, p.fsc, p.fsh, b0,
                                                      h0 - 1, w0 - 1, p.B, p.H, p.W, wtid);
-#if DSEP_LOAD_BEFORE_WAIT
-                    mbar_wait(&aempty[as_], aph ^ 1u);
-#endif
                     if (!skip) patch_store<kPatchW, kPatchH>(R, sa, sa + kPatchPlane, three, p.fsc != nullptr, p.fact);
                 }
                 publish();
@@ -739,7 +723,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             // network's maps >= 16 x 8): no per-row predicates, one 64-bit base per thread + constant strides,
             // explicit shared-space staging accesses, scale folded into the FMAs.  ~2.5x fewer instructions
             // than the generic path below (which spent ~55 per float4 on predicates and 64-bit addresses).
-#ifndef DSEP_NO_EPI_FAST
             if constexpr (HALO && NT >= 64) {
                 if (b0 < p.B && h0 + 16 <= p.H && w0 + 8 <= p.W && n0 + NT <= p.cout_store) {
                     constexpr int kChunks = NT / 64;
@@ -762,13 +745,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
                     for (int c = 0; c < kChunks; ++c) {
                         float4 res[8];
-#if !DSEP_EPI_RES_LATE
                         if (res0 != nullptr) {     // prefetch the residual while the accumulator is still being produced
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 res[i] = __ldg(reinterpret_cast<const float4*>(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half));
                         }
-#endif
                         float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.bias != nullptr) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n + c * 32));
                         if (p.film != nullptr) {
@@ -810,13 +791,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         for (int j = 0; j < 8; ++j)
                             sts128(st_base ^ (j << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         __syncwarp();
-#if DSEP_EPI_RES_LATE
-                        if (res0 != nullptr) {     // after the accumulator registers are dead (register pressure)
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                res[i] = __ldg(reinterpret_cast<const float4*>(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half));
-                        }
-#endif
                         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -842,7 +816,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     return;
                 }
             }
-#endif
 
             if constexpr (NT >= 64) {
                 constexpr int kChunks = NT / 64;          // 32-column chunks per warp

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Builds a variant of libdsep.so with extra compile-time switches for kernel experiments:
-#   tools/build_variant.sh NAME -DDSEP_NO_EPI_FAST ...   ->  diffsep_b200/build/variants/libdsep_NAME.so
+#   tools/build_variant.sh NAME -DDSEP_CONV_BK=32 ...   ->  diffsep_b200/build/variants/libdsep_NAME.so
 # run with DSEP_LIB=diffsep_b200/build/variants/libdsep_NAME.so (the build/ tree ships to the GPU box).
 set -e
 name=$1; shift
