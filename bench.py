@@ -262,7 +262,14 @@ def run_gpu(args):
                         "note": f"whole job: algorithmic FLOPs ({GFLOP_PER_EVAL} GFLOP/sample/eval x {NFE}) / wall, "
                                 "per GPU, vs sustained measured bf16 peak"}
         threads = os.cpu_count() or 1
-        cpu_dt, cpu_utt_s, cpu_nfe = cpu_sample(3 if WORKLOAD == "configs[1]" else 1, threads)
+        # the CPU baseline is taken on rank 0 at N=1 only: under torchrun the other ranks' NCCL barrier
+        # spin-waits would share the host cores with it (measured: 0.027 -> 0.002 utt/s at N=2)
+        cpu_base = None
+        if world == 1:
+            cpu_dt, cpu_utt_s, cpu_nfe = cpu_sample(3 if WORKLOAD == "configs[1]" else 1, threads)
+            cpu_base = {"value": cpu_utt_s, "unit": "utt/s", "cores": threads, "kind": "port",
+                        "sample": f"1 utterance x {cpu_nfe} of {NFE} score evaluations through "
+                                  f"the CPU oracle in {cpu_dt:.1f} s, scaled x{NFE / cpu_nfe:g}"}
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -272,10 +279,9 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": host_mix.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clock_info, "roofline": roof,
-            "cpu_baseline": {"value": cpu_utt_s, "unit": "utt/s", "cores": threads, "kind": "port",
-                             "sample": f"1 utterance x {cpu_nfe} of {NFE} score evaluations through "
-                                       f"the CPU oracle in {cpu_dt:.1f} s, scaled x{NFE / cpu_nfe:g}"},
         }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
