@@ -9,6 +9,7 @@ updates) is out of scope.
 from __future__ import annotations
 
 import math
+import warnings
 from types import SimpleNamespace
 
 import torch
@@ -19,6 +20,30 @@ from .sdes.sdes import SDERegistry
 
 _SDE_TARGETS = {"sdes.sdes.MixSDE": "mix", "sdes.sdes.PriorMixSDE": "priormix",
                 "sdes.MixSDE": "mix", "sdes.PriorMixSDE": "priormix"}
+
+
+def checkpoint_state(ckpt):
+    """``(config, score-model state_dict)`` of a loaded Lightning ``.ckpt`` / HF ``checkpoint.pt`` dict, with the EMA
+    weights swapped in as the reference does on ``.eval()`` (pl_model.py:650-670).  ``ema.shadow_params`` is a
+    list in ``parameters()`` order (output_layer first, then all_modules: ncsnpp.py:105,308 — the order of the
+    ``state_dict`` keys); torch_ema tracks only ``requires_grad`` parameters, so the frozen Fourier ``W`` and the
+    STFT window buffers are not in it."""
+    config = ckpt.get("hyper_parameters", {}).get("config")
+    sd = {k[len("score_model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("score_model.")}
+    ema = ckpt.get("ema")
+    if ema and ema.get("shadow_params"):
+        names = [k for k in sd if k.startswith("backbone.") and not k.endswith("all_modules.0.W")]
+        shadow = ema["shadow_params"]
+        if len(shadow) == len(names):
+            for k, v in zip(names, shadow):
+                if tuple(v.shape) != tuple(sd[k].shape):
+                    raise ValueError(f"EMA shadow parameter for {k} has shape {tuple(v.shape)}, "
+                                     f"the state_dict has {tuple(sd[k].shape)}")
+                sd[k] = v
+        else:
+            warnings.warn(f"checkpoint holds {len(shadow)} EMA shadow parameters for {len(names)} trainable "
+                          "tensors: EMA weights NOT applied, using the raw state_dict")
+    return config, sd
 
 
 def normalize_batch(batch):
@@ -151,17 +176,6 @@ class DiffSepModel(torch.nn.Module):
         ``state_dict`` (``score_model.*``), and — because the reference swaps EMA weights in on
         ``.eval()`` (pl_model.py:650-670) — ``ema.shadow_params`` in ``parameters()`` order."""
         ckpt = torch.load(path, map_location="cpu", weights_only=False)
-        config = ckpt.get("hyper_parameters", {}).get("config")
-        sd = {k[len("score_model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("score_model.")}
-        ema = ckpt.get("ema")
-        if ema and ema.get("shadow_params"):
-            # parameters() order: output_layer first, then all_modules (ncsnpp.py:105,308); buffers
-            # (stft windows) and the frozen Fourier W are not parameters with requires_grad... W has
-            # requires_grad=False but IS a parameter, torch_ema only tracks requires_grad ones.
-            names = [k for k in sd if k.startswith("backbone.") and not k.endswith("all_modules.0.W")]
-            shadow = ema["shadow_params"]
-            if len(shadow) == len(names):
-                for k, v in zip(names, shadow):
-                    sd[k] = v
+        config, sd = checkpoint_state(ckpt)
         model = cls(config, device=device, passes=passes, score_state_dict=sd)
         return model

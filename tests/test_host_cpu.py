@@ -195,3 +195,37 @@ def test_wav_io_round_trip(tmp_path):
     wavfile.write(tmp_path / "b.wav", 8000, (x[0].numpy() * 32768).astype(np.int16))
     z, _ = load_wav(tmp_path / "b.wav")
     assert float((z - x).abs().max()) < 1e-4
+
+
+def test_checkpoint_state_swaps_ema_weights_in():
+    """load_from_checkpoint's host logic (reference pl_model.py:642-670): the `score_model.` prefix is stripped, the
+    EMA shadow list (parameters() order, frozen Fourier W excluded) replaces the raw weights, a count mismatch
+    falls back to the raw weights with a warning, a shape mismatch is an error."""
+    import warnings
+    from oracle import weights as ow
+    from diffsep_b200.pl_model import DEFAULT_CONFIG, checkpoint_state
+    ema_sd = ow.make_score_model_state_dict(nf=32, seed=0)
+    raw = ow.make_score_model_state_dict(nf=32, seed=1)
+    names = [k for k in ema_sd if k.startswith("backbone.") and not k.endswith("all_modules.0.W")]
+    ckpt = {"state_dict": {**{"score_model." + k: v for k, v in raw.items()}, "other.module": torch.zeros(1)},
+            "hyper_parameters": {"config": DEFAULT_CONFIG},
+            "ema": {"shadow_params": [ema_sd[k] for k in names], "decay": 0.999}}
+    config, sd = checkpoint_state(ckpt)
+    assert config is DEFAULT_CONFIG and set(sd) == set(raw)
+    assert all(torch.equal(sd[k], ema_sd[k]) for k in names)
+    w = "backbone.all_modules.0.W"
+    assert torch.equal(sd[w], raw[w])                      # not tracked by torch_ema: stays raw
+    # no EMA entry: raw weights
+    _, sd2 = checkpoint_state({"state_dict": ckpt["state_dict"]})
+    assert all(torch.equal(sd2[k], raw[k]) for k in names)
+    # wrong count: warn and keep raw
+    bad = dict(ckpt, ema={"shadow_params": ckpt["ema"]["shadow_params"][:-1]})
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        _, sd3 = checkpoint_state(bad)
+    assert rec and "EMA" in str(rec[0].message) and all(torch.equal(sd3[k], raw[k]) for k in names)
+    # wrong shape: error
+    shadow = list(ckpt["ema"]["shadow_params"])
+    shadow[3] = torch.zeros(7)
+    with pytest.raises(ValueError):
+        checkpoint_state(dict(ckpt, ema={"shadow_params": shadow}))
