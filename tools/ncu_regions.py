@@ -3,7 +3,7 @@ capture of conv_tc_kernel<128, halo> to source lines and to the kernel's roles.
 
     ncu -i conv.ncu-rep --page source --csv --print-source sass > sass.csv
     cuobjdump -xelf conv_tc.sm_100a.cubin diffsep_b200/libdsep.so; nvdisasm -g -c conv_tc.sm_100a.cubin > disasm.txt
-    python tools/ncu_regions.py sass.csv disasm.txt [lines]
+    python tools/ncu_regions.py sass.csv disasm.txt [regions|lines] [conv_tc.cu of that build]
 """
 import collections
 import csv
@@ -12,7 +12,8 @@ import sys
 
 sass_csv, disasm = sys.argv[1], sys.argv[2]
 mode = sys.argv[3] if len(sys.argv) > 3 else "regions"
-src = open("diffsep_b200/csrc/conv_tc.cu").read().split("\n") if True else []
+src_path = sys.argv[4] if len(sys.argv) > 4 else "diffsep_b200/csrc/conv_tc.cu"   # the source the binary was built from
+src = open(src_path).read().split("\n")
 # role boundaries from marker comments in the source
 def find(marker):
     for i, l in enumerate(src):
