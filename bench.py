@@ -178,6 +178,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device()
     passes = int(os.environ.get("DSEP_PASSES", "3"))
+    if passes not in (1, 3):
+        raise SystemExit("DSEP_PASSES must be 3 (parity mode) or 1; the experimental e4m3-correction mode (2) is "
+                         "timed with tools/profile_conv.py until it has run on hardware")
 
     import copy
     cfg = copy.deepcopy(DEFAULT_CONFIG)

@@ -15,7 +15,7 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("DSEP_LIB") or Path(__file__).resolve().parent / "libdsep.so")
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -41,6 +41,7 @@ PROTOTYPES = {
                        _p, _i, _p],
     "dsep_split_f16": [_p, _i64, _f, _p, _p, _p],
     "dsep_conv2d_fused": [C.POINTER(ConvArgs), _p],
+    "dsep_conv2d_fused8": [C.POINTER(ConvArgs), _f, _i, _p],
     "dsep_gn_tables": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p],
     "dsep_channel_stats": [_p, _i, _i, _i, _p, _p],
     "dsep_zero": [_p, _i64, _p],
@@ -67,7 +68,7 @@ PROTOTYPES = {
     "dsep_scale_output": [_p, _p, _i, _i, _i, _p, _p],
     "dsep_randn": [_p, _i64, _u64, _u64, _p],
 }
-OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok", "dsep_conv_kblock")
+OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok", "dsep_conv_kblock", "dsep_has_fp8_corr")
 
 _lib = None
 
@@ -96,6 +97,7 @@ def load():
     lib.dsep_abi_version.restype = C.c_int
     lib.dsep_device_ok.restype = C.c_int
     lib.dsep_conv_kblock.restype = C.c_int
+    lib.dsep_has_fp8_corr.restype = C.c_int
     if lib.dsep_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libdsep.so ABI {lib.dsep_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = lib

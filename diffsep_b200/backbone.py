@@ -97,6 +97,27 @@ class ConvWeight:
             self.bias = b
 
 
+    # ---- experimental passes = 2 (libdsep built with -DDSEP_FP8_CORR=1): e4m3 correction plane
+    A8_EXP = 3            # activations enter the e4m3 planes as A_hi * 2^3 (saturating above 56) and A_lo * 2^14
+    W8_EXP = -3           # fp16 weight planes hold |W * 2^k| < 2048: W_hi * 2^-3 < 256 and W_lo * 2^8 <= 128 fit e4m3
+
+    def planes8(self) -> Split:
+        """(hi = the fp16 hi plane, lo = the e4m3 plane [taps, Cout_pad, 2 * Cin_pad] bytes viewed as fp16): per 8
+        input channels the 16 bytes [W_hi8 x 8 | W_lo8 x 8] the kernel pairs with [A_lo8 x 8 | A_hi8 x 8]."""
+        if getattr(self, "_planes8", None) is None:
+            hi, lo = self.planes.hi.float(), self.planes.lo.float()
+            t, n, c = hi.shape
+            h8 = (hi * 2.0 ** self.W8_EXP).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+            l8 = (lo * 2.0 ** (self.W8_EXP + 11)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+            w8 = torch.cat([h8.reshape(t, n, c // 8, 8), l8.reshape(t, n, c // 8, 8)], dim=-1).contiguous()
+            self._planes8 = Split(self.planes.hi, w8.view(torch.float16).reshape(t, n, c))
+        return self._planes8
+
+    @property
+    def corr_rel(self):
+        return 2.0 ** -(self.W8_EXP + self.A8_EXP + 11)
+
+
 class Arena:
     """Recycles plan buffers by exact byte size (single stream, in-order execution)."""
 
@@ -154,10 +175,17 @@ class NCSNppB200:
         ops.require_device()
         self.device = torch.device(device)
         self.nf, self.ch_in, self.ch_out, self.passes = nf, ch_in, ch_out, passes
+        if passes == 2:
+            from . import _lib
+            if not _lib.load().dsep_has_fp8_corr():
+                raise NotImplementedError("passes=2 (e4m3 correction products) needs libdsep built with "
+                                          "-DDSEP_FP8_CORR=1 (tools/build_variant.sh, DSEP_LIB)")
+        # convs that still take operand planes (small maps, FIR-resampled inputs, narrow outputs) stay at 3 products
+        self.plane_passes = 3 if passes == 2 else passes
         # in-kernel GroupNorm/SiLU/concat prologue (dsep_conv2d_fused) where shapes allow.  With three
         # MMA passes per tile the worker warps have time to build the patches for free; with one pass
         # they would become the bottleneck (measured), so that mode keeps the separate pass.
-        default_fuse = "1" if passes == 3 else "0"
+        default_fuse = "1" if passes in (2, 3) else "0"
         self.fuse = bool(int(os.environ.get("DSEP_FUSE", default_fuse))) if fuse is None else bool(fuse)
         self.temb_dim = 4 * nf
         self._plans = {}
@@ -343,7 +371,7 @@ class _Plan:
         self.steps.append(lambda: ops.conv2d_tc(
             a() if callable(a) else a, B, H, W, cin_pad, cw.planes, cw.cout_pad, cw.ksize, out, cout_store,
             bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
-            acc_scale=cw.acc_scale, passes=net.passes, a2=a2, Cin2=cin2, w2=w2, stats=stats))
+            acc_scale=cw.acc_scale, passes=net.plane_passes, a2=a2, Cin2=cin2, w2=w2, stats=stats))
 
     def _fusable(self, H, W, *channels):
         """dsep_conv2d_fused's in-kernel prologue: map of at least 16 x 8, 64-channel granularity"""
@@ -368,10 +396,17 @@ class _Plan:
         if shortcut_raw is not None:
             s0, S0, s1, S1 = shortcut_raw
             kw = dict(s0=s0, S0=S0, s1=s1, S1=S1, Cin2=cw.cin2_pad, w2=cw.planes2)
+        if net.passes == 2 and cw.cout_pad >= 64:      # experimental: fp16 hi*hi + one e4m3 correction product
+            self.steps.append(lambda: ops.conv2d_fused(
+                B, H, W, cin, cw.planes8(), cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1,
+                sc=sc, sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=stride, residual=residual,
+                scale=scale, acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
+                a8_exp=cw.A8_EXP, **kw))
+            return
         self.steps.append(lambda: ops.conv2d_fused(
             B, H, W, cin, cw.planes, cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1, sc=sc,
             sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
-            acc_scale=cw.acc_scale, stats=stats, passes=net.passes, **kw))
+            acc_scale=cw.acc_scale, stats=stats, passes=net.plane_passes, **kw))
 
     def _resblock(self, rb, x: Act, skip: Act = None, mode=0, want_stats=True) -> Act:
         """ResnetBlockBigGANpp (layerspp.py:291-323).  mode 0 plain, 1 up, 2 down.

@@ -64,6 +64,10 @@ struct ConvParams {
     const float* fx0; const float* fx1; int fC0, fC1;
     const float* fsc; const float* fsh; int fact;
     const float* gx0; const float* gx1; int gC0, gC1;
+#if DSEP_FP8_CORR
+    float corr_rel;        // passes = 2: weight of the e4m3 correction accumulator relative to the fp16 one
+    float a8_hi, a8_lo;    // passes = 2: power-of-two prescales of the e4m3 activation planes (A_hi, A_lo)
+#endif
     int debug;             // DSEP_CONV_DEBUG bitmask: 1 skip MMA issue, 2 skip TMA loads, 4 skip epilogue stores (timing experiments)
 };
 
@@ -74,6 +78,14 @@ constexpr int kThreads = 128 + kEpiWarps * 32;
 // delivery (~12.6 TB/s with 128-byte rows, ~7 TB/s with 64-byte rows), not by ring depth.
 #ifndef DSEP_CONV_BK
 #define DSEP_CONV_BK 64
+#endif
+// Build switch (off: the shipped binary does not contain this path).  1 adds passes = 2 to the halo kernel with
+// in-kernel prologue: per K=16 step ONE fp16 product hi*hi plus ONE e4m3 tensor-core product that carries both
+// correction terms, [A_lo8 | A_hi8] x [W_hi8 ; W_lo8] (K = 32 bytes, twice the fp16 rate) = 2 tensor-core units
+// per MAC instead of 3.  tools/numerics_study.py: network error 4.7e-5 from the operand rounding (budget 1e-4;
+// dropping either correction in a single level-0 conv costs 2.4e-4).  Compiles; NOT yet run on hardware.
+#ifndef DSEP_FP8_CORR
+#define DSEP_FP8_CORR 0
 #endif
 constexpr int kBK = DSEP_CONV_BK;
 static_assert(kBK == 32 || kBK == 64, "K-block must be 32 or 64 channels");
@@ -208,9 +220,20 @@ __device__ __forceinline__ void patch_load(PatchRegs<PW, PH>& R, const float* x0
 
 // phase 2: y = act(x * sc + sh) (zero outside the image: the conv pads the ACTIVATED tensor), fp32 -> (hi, lo)
 // fp16 split, 128-byte-swizzled K-major rows.  dst_hi / dst_lo are shared-window addresses of the two planes.
+#if DSEP_FP8_CORR
+// 8 activations -> 16 bytes of the e4m3 correction plane: [A_lo8 x 8 | A_hi8 x 8] (the weight plane holds
+// [W_hi8 x 8 | W_lo8 x 8] at the same bytes, so the K = 32 product sums A_lo*W_hi + A_hi*W_lo)
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
+    uint16_t p0, p1;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p0) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p1) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(p0) | (static_cast<uint32_t>(p1) << 16);
+}
+#endif
+
 template <int PW, int PH>
 __device__ __forceinline__ void patch_store(const PatchRegs<PW, PH>& R, uint32_t dst_hi, uint32_t dst_lo, bool want_lo,
-                                            bool affine, int act) {
+                                            bool affine, int act, float a8_hi = 0.f, float a8_lo = 0.f) {
     using PR = PatchRegs<PW, PH>;
     if (!R.active) return;
 #pragma unroll
@@ -236,6 +259,21 @@ __device__ __forceinline__ void patch_store(const PatchRegs<PW, PH>& R, uint32_t
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
+#if DSEP_FP8_CORR
+            if (a8_hi != 0.f) {      // second plane = e4m3 corrections instead of the fp16 lo plane
+                float h[8], l[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+                    h[2 * e] = b.x; h[2 * e + 1] = b.y;
+                    l[2 * e] = y[2 * e] - b.x; l[2 * e + 1] = y[2 * e + 1] - b.y;
+                }
+                lo[0] = e4m3x4(l[0] * a8_lo, l[1] * a8_lo, l[2] * a8_lo, l[3] * a8_lo);
+                lo[1] = e4m3x4(l[4] * a8_lo, l[5] * a8_lo, l[6] * a8_lo, l[7] * a8_lo);
+                lo[2] = e4m3x4(h[0] * a8_hi, h[1] * a8_hi, h[2] * a8_hi, h[3] * a8_hi);
+                lo[3] = e4m3x4(h[4] * a8_hi, h[5] * a8_hi, h[6] * a8_hi, h[7] * a8_hi);
+            }
+#endif
         }
         sts128(dst_hi + off, hi[0], hi[1], hi[2], hi[3]);
         if (want_lo) sts128(dst_lo + off, lo[0], lo[1], lo[2], lo[3]);
@@ -275,7 +313,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler too
     const int lane = threadIdx.x & 31;
+#if DSEP_FP8_CORR
+    const bool three = p.passes != 1;        // two operand planes per stage (fp16 lo, or the e4m3 correction plane)
+    const bool fp8c = p.passes == 2;         // main K-blocks: hi*hi in fp16 + both corrections in one e4m3 product
+#else
     const bool three = p.passes == 3;
+#endif
     // CTA pair: the two CTAs of a cluster work on M-adjacent tiles of the same channel tile, each
     // fetches half of every weight tile and multicasts it to both (halves the weight traffic)
     const uint32_t rank = cluster_ctarank();
@@ -352,13 +395,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             patch_load<8, 16>(R, p.fx0, p.fC0, p.fx1, p.fC1, pi - p.kblocks2, p.fsc, p.fsh, b0, h0, w0,
                                               p.B, p.H, p.W, wtid);
                     }
+#if DSEP_FP8_CORR
+                    if (!skip)
+                        patch_store<8, 16>(R, sa, sa + kPatchPlane, three, !second && p.fsc != nullptr, p.fact,
+                                           (fp8c && !second) ? p.a8_hi : 0.f, p.a8_lo);
+#else
                     if (!skip) patch_store<8, 16>(R, sa, sa + kPatchPlane, three, !second && p.fsc != nullptr, p.fact);
+#endif
                 } else {
                     PatchRegs<kPatchW, kPatchH> R;
                     if (!skip)
                         patch_load<kPatchW, kPatchH>(R, p.fx0, p.fC0, p.fx1, p.fC1, pi - p.kblocks2, p.fsc, p.fsh, b0,
                                                      h0 - 1, w0 - 1, p.B, p.H, p.W, wtid);
+#if DSEP_FP8_CORR
+                    if (!skip)
+                        patch_store<kPatchW, kPatchH>(R, sa, sa + kPatchPlane, three, p.fsc != nullptr, p.fact,
+                                                      fp8c ? p.a8_hi : 0.f, p.a8_lo);
+#else
                     if (!skip) patch_store<kPatchW, kPatchH>(R, sa, sa + kPatchPlane, three, p.fsc != nullptr, p.fact);
+#endif
                 }
                 publish();
             }
@@ -506,8 +561,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 2 * NT;
                     uint32_t accumulate = 0;
+#if DSEP_FP8_CORR
+                    uint32_t accumulate8 = 0;        // first e4m3 product of the tile initialises columns [NT, 2NT)
+#endif
                     // one weight stage against the A rows whose hi-plane descriptor word is a_word
-                    auto issue = [&](uint32_t a_word, uint32_t a_hiword) {
+                    auto issue = [&](uint32_t a_word, uint32_t a_hiword, bool main_kb) {
                         mbar_wait(&full[bs], bph);
                         tc_fence_after();
                         const uint32_t b_word = b_ring + bs * (HCfg::kBStage >> 4);   // W_hi rows, then W_lo rows
@@ -519,6 +577,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                                     const uint64_t b_hi = desc(b_word + 2 * k, kHiPlain);
                                     // TWO: region X (this CTA's half of [W_hi ; W_lo]) / region Y (its half of W_hi)
                                     const uint64_t b_y = TWO ? desc(b_word + (HCfg::kBBytes >> 4) + 2 * k, kHiPlain) : b_hi;
+#if DSEP_FP8_CORR
+                                    if (fp8c) {
+                                        const uint64_t a_2 = desc(a_word + (kPatchPlane >> 4) + 2 * k, a_hiword);
+                                        const uint64_t b_2 = desc(b_word + (HCfg::kBBytes >> 4) + 2 * k, kHiPlain);
+                                        mma(d_tmem, a_hi, b_hi, idesc_n, accumulate);              // hi*hi -> [0, NT)
+                                        if (main_kb) {     // [A_lo8 | A_hi8] x [W_hi8 ; W_lo8], K = 32 -> [NT, 2NT)
+                                            umma_e4m3(d_tmem + NT, a_2, b_2, idesc_n, accumulate8);
+                                            accumulate8 = 1;
+                                        } else {           // fp16 shortcut K-block: all three products into [0, NT)
+                                            mma(d_tmem, a_hi, b_2, idesc_n, 1);
+                                            mma(d_tmem, a_2, b_hi, idesc_n, 1);
+                                        }
+                                    } else
+#endif
                                     if (three) {
                                         mma(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
                                         mma(d_tmem, desc(a_word + (kPatchPlane >> 4) + 2 * k, a_hiword), b_y, idesc_n, 1);
@@ -536,7 +608,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     for (int kb = 0; kb < p.kblocks2; ++kb) {      // fused 1x1 shortcut K-blocks
                         mbar_wait(&afull[as_], aph);
                         tc_fence_after();
-                        issue(a_ring + as_ * (HCfg::kAStage >> 4), kHiPlain);
+                        issue(a_ring + as_ * (HCfg::kAStage >> 4), kHiPlain, false);
                         if (leader) commit_local(&aempty[as_]);
                         __syncwarp();
                         if (++as_ == NA) { as_ = 0; aph ^= 1u; }
@@ -548,9 +620,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         if (p.taps == 9) {
 #pragma unroll
                             for (int tap = 0; tap < 9; ++tap)
-                                issue(sa + ((tap / 3) * kPatchW + tap % 3) * 8, kHiPatch);
+                                issue(sa + ((tap / 3) * kPatchW + tap % 3) * 8, kHiPatch, true);
                         } else {
-                            issue(sa, kHiPlain);
+                            issue(sa, kHiPlain, true);
                         }
                         if (leader) commit_local(&aempty[as_]);
                         __syncwarp();
@@ -663,6 +735,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if constexpr (HALO) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int ew = warp - 4;
         const int wq = ew & 3;                // TMEM lane quarter == warp_id % 4
+        // sum of the two accumulator halves: hi*hi (+ lo*hi) and hi*lo — or, with e4m3 corrections, the correction
+        // accumulator weighted by the ratio of the operand prescales
+#if DSEP_FP8_CORR
+        const float crel = fp8c ? p.corr_rel : 1.0f;
+#define EPI_ADD(main_, corr_) fmaf((corr_), crel, (main_))
+#else
+#define EPI_ADD(main_, corr_) ((main_) + (corr_))
+#endif
         const int tw_mask = (1 << p.tw_log2) - 1, th_mask = (1 << p.th_log2) - 1;
         // GroupNorm partial sums of this thread's 4 channels, carried across consecutive tiles of the
         // same (batch entry, channel tile) and flushed with fp64 atomics only when that changes
@@ -774,7 +854,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
-                                    v[hh * 16 + j] = __float_as_uint(__uint_as_float(v[hh * 16 + j]) + __uint_as_float(u[j]));
+                                    v[hh * 16 + j] = __float_as_uint(EPI_ADD(__uint_as_float(v[hh * 16 + j]), __uint_as_float(u[j])));
                             }
                         } else {
                             tmem_ld_wait();
@@ -865,7 +945,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                v[hh * 16 + j] = __float_as_uint(__uint_as_float(v[hh * 16 + j]) + __uint_as_float(u[j]));
+                                v[hh * 16 + j] = __float_as_uint(EPI_ADD(__uint_as_float(v[hh * 16 + j]), __uint_as_float(u[j])));
                         }
                     } else {
                         tmem_ld_wait();
@@ -939,7 +1019,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         tmem_ld_32x16(t_addr + NT, u);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(EPI_ADD(__uint_as_float(v[j]), __uint_as_float(u[j])));
                     } else {
                         tmem_ld_wait();
                     }
@@ -1003,6 +1083,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
+
+#undef EPI_ADD
 
 // ------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1086,14 +1168,22 @@ static int ilog2(int v) {
 
 extern "C" int dsep_conv_kblock(void) { return dsep::kBK; }
 
-extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) {
+// corr_rel / a8_exp: only for passes = 2 (dsep_conv2d_fused8); dsep_conv2d_fused passes (1, 0)
+static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, dsep_stream_t stream) {
     using namespace dsep;
     DSEP_REQUIRE(g != nullptr, "conv2d: null argument block");
     const int B = g->B, H = g->H, W = g->W, Cin = g->Cin, Cout_pad = g->Cout_pad, ksize = g->ksize;
     const int Cin2 = g->Cin2, cout_store = g->cout_store, passes = g->passes;
     const bool main_fused = g->x0 != nullptr, short_fused = g->s0 != nullptr;
     DSEP_REQUIRE((g->a_hi || main_fused) && g->w_hi && g->out, "conv2d_tc: null operand");
+#if DSEP_FP8_CORR
+    DSEP_REQUIRE(passes == 1 || passes == 2 || passes == 3, "conv2d_tc: passes must be 1, 2 or 3 (got %d)", passes);
+    DSEP_REQUIRE(passes != 2 || (main_fused && Cout_pad % 64 == 0 && H >= 16 && W >= 8 && corr_rel > 0.f),
+                 "conv2d_fused8: e4m3 corrections need the in-kernel prologue, Cout >= 64 and a map of at least 16 x 8");
+#else
     DSEP_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3 (got %d)", passes);
+    (void)corr_rel; (void)a8_exp;
+#endif
     DSEP_REQUIRE(passes == 1 || ((g->a_lo || main_fused) && g->w_lo), "conv2d_tc: passes=3 needs the lo planes");
     DSEP_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize must be 1 or 3 (got %d)", ksize);
     DSEP_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_tc: empty tensor");
@@ -1154,6 +1244,11 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
     p.scale = g->scale; p.acc_scale = g->acc_scale; p.out = g->out; p.stats = g->stats;
     p.fx0 = g->x0; p.fx1 = g->x1; p.fC0 = g->C0; p.fC1 = g->C1; p.fsc = g->sc; p.fsh = g->sh; p.fact = g->act;
     p.gx0 = g->s0; p.gx1 = g->s1; p.gC0 = g->S0; p.gC1 = g->S1;
+#if DSEP_FP8_CORR
+    p.corr_rel = corr_rel;
+    p.a8_hi = ldexpf(1.0f, a8_exp);
+    p.a8_lo = ldexpf(1.0f, a8_exp + 11);
+#endif
     {
         static const int dbg = getenv("DSEP_CONV_DEBUG") ? atoi(getenv("DSEP_CONV_DEBUG")) : 0;
         p.debug = dbg;
@@ -1167,7 +1262,7 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin * 2};
         const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
         if ((rc = make_map(&m.w_hi, g->w_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
-        if (passes == 3) {
+        if (passes != 1) {
             if ((rc = make_map(&m.w_lo, g->w_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         } else {
             m.w_lo = m.w_hi;
@@ -1178,7 +1273,7 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
             const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)(patch3 ? kPatchW : tw),
                                         (cuuint32_t)(patch3 ? kPatchH : th), (cuuint32_t)tb};
             if ((rc = make_map(&m.a_hi, g->a_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
-            if (passes == 3) {
+            if (passes != 1) {
                 if ((rc = make_map(&m.a_lo, g->a_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
             } else {
                 m.a_lo = m.a_hi;
@@ -1193,7 +1288,7 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
         const cuuint64_t wstr[1] = {(cuuint64_t)Cin2 * 2};
         const cuuint32_t wbox[2] = {(cuuint32_t)kBK, (cuuint32_t)(NT / 2)};
         if ((rc = make_map(&m.w2_hi, g->w2_hi, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
-        if (passes == 3) {
+        if (passes != 1) {
             if ((rc = make_map(&m.w2_lo, g->w2_lo, 2, wdims, wstr, wbox)) != DSEP_OK) return rc;
         } else {
             m.w2_lo = m.w2_hi;
@@ -1203,7 +1298,7 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
             const cuuint64_t astr[3] = {(cuuint64_t)Cin2 * 2, (cuuint64_t)W * Cin2 * 2, (cuuint64_t)H * W * Cin2 * 2};
             const cuuint32_t abox[4] = {(cuuint32_t)kBK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
             if ((rc = make_map(&m.a2_hi, g->a2_hi, 4, adims, astr, abox)) != DSEP_OK) return rc;
-            if (passes == 3) {
+            if (passes != 1) {
                 if ((rc = make_map(&m.a2_lo, g->a2_lo, 4, adims, astr, abox)) != DSEP_OK) return rc;
             } else {
                 m.a2_lo = m.a2_hi;
@@ -1213,6 +1308,9 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
     if (halo && NT == 16) return launch_conv<16, true>(m, p, s);
+#if DSEP_FP8_CORR
+    if (passes == 2) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);
+#endif
     if (halo && two_env)
         return NT == 64 ? launch_conv<64, true, true>(m, p, s) : launch_conv<128, true, true>(m, p, s);
     if (halo) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);
@@ -1221,6 +1319,24 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
         case 64: return launch_conv<64, false>(m, p, s);
         default: return launch_conv<128, false>(m, p, s);
     }
+}
+
+extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) {
+    DSEP_REQUIRE(g == nullptr || g->passes != 2, "conv2d_fused: passes = 2 goes through dsep_conv2d_fused8");
+    return conv_dispatch(g, 1.0f, 0, stream);
+}
+
+extern "C" int dsep_has_fp8_corr(void) { return DSEP_FP8_CORR; }
+
+extern "C" int dsep_conv2d_fused8(const dsep_conv_args* g, float corr_rel, int a8_exp, dsep_stream_t stream) {
+#if DSEP_FP8_CORR
+    DSEP_REQUIRE(g != nullptr && g->passes == 2, "conv2d_fused8: passes must be 2");
+    return conv_dispatch(g, corr_rel, a8_exp, stream);
+#else
+    (void)g; (void)corr_rel; (void)a8_exp; (void)stream;
+    dsep::set_error("conv2d_fused8: this libdsep.so was built without DSEP_FP8_CORR");
+    return DSEP_ERR_UNSUPPORTED;
+#endif
 }
 
 extern "C" int dsep_conv2d_tc(const void* a_hi, const void* a_lo, int B, int H, int W, int Cin,

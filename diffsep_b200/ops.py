@@ -84,9 +84,10 @@ def conv2d_tc(a: Split, B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store
 def conv2d_fused(B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store, a: Split = None, x0=None, C0=0, x1=None,
                  C1=0, sc=None, sh=None, act=0, a2: Split = None, s0=None, S0=0, s1=None, S1=0, Cin2=0,
                  w2: Split = None, bias=None, film=None, film_stride=0, residual=None, scale=1.0, acc_scale=1.0,
-                 stats=None, passes=3):
+                 stats=None, passes=3, corr_rel=1.0, a8_exp=0):
     """dsep_conv2d_fused: the convolution with GroupNorm-apply / SiLU / concat / split of its operands
-    done in-kernel (x0[, x1] with sc, sh) instead of arriving as split planes (a)."""
+    done in-kernel (x0[, x1] with sc, sh) instead of arriving as split planes (a).  passes = 2
+    (experimental -DDSEP_FP8_CORR build only): dsep_conv2d_fused8, ``w.lo`` is the e4m3 correction plane."""
     _f32(out, "out"); _f32(bias, "bias"); _f32(film, "film"); _f32(residual, "residual")
     _f32(x0, "x0"); _f32(x1, "x1"); _f32(s0, "s0"); _f32(s1, "s1"); _f32(sc, "sc"); _f32(sh, "sh")
     g = _lib.ConvArgs(
@@ -96,7 +97,12 @@ def conv2d_fused(B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store, a: Sp
         ptr(w2.lo) if w2 else None, ptr(bias), film.data_ptr() if film is not None else None, film_stride,
         ptr(residual), scale, acc_scale, ptr(out), cout_store, ptr(stats), passes)
     try:
-        call("dsep_conv2d_fused", C.byref(g), stream())
+        if passes == 2:
+            call("dsep_conv2d_fused8", C.byref(g), corr_rel, a8_exp, stream())
+        else:
+            call("dsep_conv2d_fused", C.byref(g), stream())
+    except NotImplementedError:      # a RuntimeError subclass: keep the reference's exception type
+        raise
     except RuntimeError as e:
         desc = {k: getattr(g, k) for k, t in g._fields_ if t is C.c_int or t is C.c_float}
         desc.update({k: bool(getattr(g, k)) for k, t in g._fields_ if t is C.c_void_p})

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 4
+#define DSEP_ABI_VERSION 5
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -101,6 +101,16 @@ typedef struct {
     int passes;
 } dsep_conv_args;
 int dsep_conv2d_fused(const dsep_conv_args* args, dsep_stream_t stream);
+/* Experimental build switch -DDSEP_FP8_CORR=1 (dsep_has_fp8_corr() == 1; off in the shipped binary, where this
+ * entry point returns DSEP_ERR_UNSUPPORTED): the same fused convolution with passes = 2 — per K = 16 step one fp16
+ * product hi*hi plus ONE e4m3 tensor-core product carrying both correction terms (2 tensor-core units per MAC
+ * instead of 3; tools/numerics_study.py).  args->w_lo then points to the e4m3 weight plane [taps, Cout_pad, 2*Cin]
+ * bytes: per 8 input channels the 16 bytes [W_hi8 x 8 | W_lo8 x 8], W_hi8 = e4m3(W_hi * 2^q), W_lo8 =
+ * e4m3(W_lo * 2^(q+11)) on top of the fp16 planes' prescale; activations are prescaled in-kernel by 2^a8_exp
+ * (hi) and 2^(a8_exp+11) (lo); corr_rel = 2^-(q + a8_exp + 11) weighs the correction accumulator.  A fused 1x1
+ * shortcut keeps fp16 (hi, lo) planes.  Needs x0 (in-kernel prologue), Cout >= 64, a map of at least 16 x 8. */
+int dsep_conv2d_fused8(const dsep_conv_args* args, float corr_rel, int a8_exp, dsep_stream_t stream);
+int dsep_has_fp8_corr(void);
 /* Per-(batch entry, channel) GroupNorm scale / shift from per-channel sums of a (concatenated) input:
  * sc = gamma * rstd[group], sh = beta - mean[group] * sc, so that GN(x) = x * sc + sh.  sc, sh: [B, C0+C1]. */
 int dsep_gn_tables(const double* st0, int C0, const double* st1, int C1, int B, int P, int groups,

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS)
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_abi_argument_counts_match_header():
@@ -229,3 +229,55 @@ def test_checkpoint_state_swaps_ema_weights_in():
     shadow[3] = torch.zeros(7)
     with pytest.raises(ValueError):
         checkpoint_state(dict(ckpt, ema={"shadow_params": shadow}))
+
+
+def test_fp8_correction_entry_point_is_gated(lib):
+    """The experimental e4m3-correction mode is a build switch: the shipped library exports the entry point but
+    answers DSEP_ERR_UNSUPPORTED (-> NotImplementedError), and the regular entry point rejects passes = 2."""
+    import ctypes as C
+    from diffsep_b200 import _lib
+    if lib.dsep_has_fp8_corr():
+        pytest.skip("this libdsep has the e4m3-correction mode")
+    g = _lib.ConvArgs()
+    g.passes = 2
+    with pytest.raises(NotImplementedError):
+        _lib.call("dsep_conv2d_fused8", C.byref(g), 2.0 ** -11, 3, None)
+    with pytest.raises(ValueError):
+        _lib.call("dsep_conv2d_fused", C.byref(g), None)
+
+
+def test_fp8_correction_planes_and_scales_reproduce_the_product():
+    """Host side of the e4m3-correction mode (ConvWeight.planes8 / corr_rel / A8_EXP), checked by emulating the
+    kernel's arithmetic in float64: acc_scale * (A_hi . W_hi + corr_rel * ([A_lo8 | A_hi8] . [W_hi8 ; W_lo8]))
+    equals A . W to ~1e-5, with the bytes laid out as include/dsep.h documents (16-byte groups of 8 channels)."""
+    from diffsep_b200.backbone import ConvWeight, _prescale_exp
+    from diffsep_b200.ops import Split
+    g = torch.Generator().manual_seed(3)
+    cout, cin = 64, 128
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    k = _prescale_exp(float(w.abs().max()))
+    ws = w * 2.0 ** k
+    w_hi = ws.half()
+    w_lo = (ws - w_hi.float()).half()
+    cw = object.__new__(ConvWeight)
+    cw.planes = Split(w_hi.reshape(1, cout, cin), w_lo.reshape(1, cout, cin))
+    p8 = cw.planes8()
+    assert p8.hi is cw.planes.hi and p8.lo.shape == (1, cout, cin) and p8.lo.dtype == torch.float16
+    raw = p8.lo.view(torch.uint8).reshape(cout, cin // 8, 16)
+    dec = raw.view(torch.float8_e4m3fn).double()
+    w_hi8, w_lo8 = dec[..., :8].reshape(cout, cin), dec[..., 8:].reshape(cout, cin)
+    assert torch.allclose(w_hi8, w_hi.double() * 2.0 ** cw.W8_EXP, rtol=2.0 ** -4, atol=2.0 ** -9)
+    assert float(w_hi8.abs().max()) <= 448 and float(w_lo8.abs().max()) <= 448
+    # activations as the kernel's builder prepares them (SiLU outputs up to a few units)
+    a = torch.randn(256, cin, generator=g)
+    a = a * torch.sigmoid(a) * 3.0
+    a_hi = a.half().float()
+    e4 = lambda v: v.clamp(-448, 448).to(torch.float8_e4m3fn).double()
+    a_hi8, a_lo8 = e4(a_hi * 2.0 ** cw.A8_EXP), e4((a - a_hi) * 2.0 ** (cw.A8_EXP + 11))
+    main = a_hi.double() @ w_hi.double().T
+    corr = a_lo8 @ w_hi8.T + a_hi8 @ w_lo8.T
+    got = 2.0 ** -k * (main + cw.corr_rel * corr)
+    ref = a.double() @ w.double().T
+    err = float((got - ref).norm() / ref.norm())
+    err_1pass = float((2.0 ** -k * main - ref).norm() / ref.norm())
+    assert err < 2e-5 < 2e-4 < err_1pass, (err, err_1pass)

@@ -38,7 +38,7 @@ def split(ops, x, prescale=1.0):
 def test_library_loaded_and_device_ok():
     from diffsep_b200 import _lib
     lib = _lib.load()
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 5
     assert lib.dsep_device_ok() == 1
 
 
@@ -267,6 +267,68 @@ def test_conv2d_fused_narrow_output(shape):
                      bias=cw.bias, residual=cl(res), acc_scale=cw.acc_scale)
     torch.cuda.synchronize()
     assert rel_l2(nchw(out), ref) < 1e-5
+
+
+def _needs_fp8_corr():
+    from diffsep_b200 import _lib
+    if not _lib.load().dsep_has_fp8_corr():
+        pytest.skip("experimental e4m3-correction mode: needs libdsep built with -DDSEP_FP8_CORR=1 (DSEP_LIB)")
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 128, 128, 0), (1, 16, 40, 64, 128, 64), (1, 48, 16, 256, 64, 0)])
+def test_conv2d_fused8_e4m3_corrections(shape):
+    """passes = 2: conv3x3(SiLU(GN(x))) [+ fp16 1x1 shortcut] with hi*hi in fp16 and both correction terms in ONE
+    e4m3 tensor-core product, vs float64.  Operand error: the corrections (2^-11 of the result) carry 4
+    significand bits -> ~2^-16 per term; tolerance 3e-5 per conv (tools/numerics_study.py: 4.7e-5 over the net)."""
+    _needs_fp8_corr()
+    ops = _ops()
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, Cin, Cout, Cs = shape
+    g = cases.gen(sum(shape) + 3)
+    x = torch.randn(B, Cin, H, W, generator=g) * 1.2 + 0.1
+    gamma = 1 + 0.1 * torch.randn(Cin, generator=g)
+    beta = 0.1 * torch.randn(Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    a_ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    a_ref = a_ref * torch.sigmoid(a_ref)
+    ref = F.conv2d(a_ref, w.double(), b1.double(), padding=1)
+    shortcut, kw = None, {}
+    d0 = cl(x)
+    if Cs:
+        xs = torch.randn(B, Cs, H, W, generator=g) * 3.0
+        w2 = torch.randn(Cout, Cs, 1, 1, generator=g) / math.sqrt(Cs)
+        shortcut = (w2, None)
+        ref = ref + F.conv2d(xs.double(), w2.double())
+    cw = ConvWeight(w, b1, DEV, shortcut=shortcut)
+    if Cs:
+        kw = dict(s0=cl(xs), S0=Cs, Cin2=cw.cin2_pad, w2=cw.planes2)
+    st0 = torch.empty(B, Cin, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, Cin, B, H * W, st0)
+    sc = torch.empty(B, Cin, device=DEV)
+    sh = torch.empty(B, Cin, device=DEV)
+    ops.gn_tables(st0, Cin, None, 0, B, H * W, 32, gamma.to(DEV), beta.to(DEV), 1e-6, sc, sh)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    stats = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    ops.conv2d_fused(B, H, W, Cin, cw.planes8(), cw.cout_pad, 3, out, Cout, x0=d0, C0=Cin, sc=sc, sh=sh, act=1,
+                     bias=cw.bias, acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
+                     a8_exp=cw.A8_EXP, **kw)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(out), ref) < 3e-5
+    got = nchw(out).double()
+    assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
+
+
+def test_conv2d_fused8_unsupported_on_the_shipped_build():
+    from diffsep_b200 import _lib
+    if _lib.load().dsep_has_fp8_corr():
+        pytest.skip("this libdsep has the e4m3-correction mode")
+    ops = _ops()
+    w = ops.Split.zeros((9, 64, 64), DEV)
+    x = torch.zeros(1, 16, 8, 64, device=DEV)
+    with pytest.raises(NotImplementedError):
+        ops.conv2d_fused(1, 16, 8, 64, w, 64, 3, torch.empty(1, 16, 8, 64, device=DEV), 64, x0=x, C0=64, passes=2,
+                         corr_rel=2.0 ** -11, a8_exp=3)
 
 
 def test_conv2d_fused_rejects_small_maps():

@@ -39,7 +39,12 @@ fused_in = int(os.environ.get("DSEP_FUSEDIN", "0"))
 stats = torch.zeros(B, COUT, 2, dtype=torch.float64, device=dev) if with_stats else None
 sc = torch.ones(B, CIN, device=dev)
 sh = torch.zeros(B, CIN, device=dev)
-if fused_in:
+if fused_in and passes == 2:      # experimental e4m3-correction mode (DSEP_LIB = a -DDSEP_FP8_CORR=1 build)
+    run = lambda: ops.conv2d_fused(B, H, W, CIN, cw.planes8(), cw.cout_pad, K, out, COUT, x0=x, C0=CIN, sc=sc, sh=sh,
+                                   act=1, bias=cw.bias, residual=res, scale=0.7071 if with_res else 1.0,
+                                   acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
+                                   a8_exp=cw.A8_EXP)
+elif fused_in:
     run = lambda: ops.conv2d_fused(B, H, W, CIN, cw.planes, cw.cout_pad, K, out, COUT, x0=x, C0=CIN, sc=sc, sh=sh,
                                    act=1, bias=cw.bias, residual=res, scale=0.7071 if with_res else 1.0,
                                    acc_scale=cw.acc_scale, stats=stats, passes=passes)
