@@ -178,9 +178,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device()
     passes = int(os.environ.get("DSEP_PASSES", "3"))
-    if passes not in (1, 3):
-        raise SystemExit("DSEP_PASSES must be 3 (parity mode) or 1; the experimental e4m3-correction mode (2) is "
-                         "timed with tools/profile_conv.py until it has run on hardware")
+    if passes not in (1, 2, 3):
+        raise SystemExit("DSEP_PASSES must be 3 (parity mode), 1 (TF32-grade) or 2 (experimental e4m3 corrections: "
+                         "needs DSEP_LIB = a -DDSEP_FP8_CORR=1 build of libdsep)")
 
     import copy
     cfg = copy.deepcopy(DEFAULT_CONFIG)
@@ -276,8 +276,9 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (3 x fp16 tensor-core passes, fp32 accumulate)" if passes == 3
-            else "fp16 operands (TF32-grade), fp32 accumulate",
+            "vs_baseline": None, "dtype": {3: "f32 (3 x fp16 tensor-core passes, fp32 accumulate)",
+                                           2: "f32 (fp16 hi*hi + e4m3 correction products, fp32 accumulate)",
+                                           1: "fp16 operands (TF32-grade), fp32 accumulate"}[passes],
             "data": "synthetic", "config": config_dict(world),
             "e2e": {"value": e2e, "unit": "utt/s", "h2d_bytes_per_step": host_mix.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
@@ -308,7 +309,13 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
     stats = torch.zeros(B, Cc, 2, dtype=torch.float64, device=dev)
     out = torch.empty(B, H, W, Cc, device=dev)
     cw = rb["conv0"]
-    if bb.fuse:
+    if bb.fuse and passes == 2:
+        run = lambda: ops.conv2d_fused(B, H, W, Cc, cw.planes8(), cw.cout_pad, 3, out, Cc, x0=x, C0=Cc, sc=sc, sh=sh,
+                                       act=1, bias=cw.bias, film=film, film_stride=Cc, acc_scale=cw.acc_scale,
+                                       stats=stats, passes=2, corr_rel=cw.corr_rel, a8_exp=cw.A8_EXP)
+        variant = ("fp32 input, GN+SiLU+split prologue in-kernel (fp16 hi + e4m3 correction planes), FiLM + GN "
+                   "statistics in the epilogue")
+    elif bb.fuse:
         run = lambda: ops.conv2d_fused(B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, x0=x, C0=Cc, sc=sc, sh=sh,
                                        act=1, bias=cw.bias, film=film, film_stride=Cc, acc_scale=cw.acc_scale,
                                        stats=stats, passes=passes)
@@ -335,8 +342,9 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
     # for reference: the same convolution fed with ready-made operand planes (no prologue, no statistics)
     ap = ops.Split.empty((B, H, W, Cc), dev)
     ops.split_f16(x, ap)
+    plane_passes = 3 if passes == 2 else passes       # operand planes carry fp16 (hi, lo) only
     ms_planes = time_it(lambda: ops.conv2d_tc(ap, B, H, W, Cc, cw.planes, cw.cout_pad, 3, out, Cc, bias=cw.bias,
-                                              acc_scale=cw.acc_scale, passes=passes))
+                                              acc_scale=cw.acc_scale, passes=plane_passes))
     flops = 2.0 * B * H * W * 9 * Cc * Cc
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops", 1590.0)
@@ -348,6 +356,7 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "ms_per_launch": ms, "algorithmic_gflop_per_launch": flops / 1e9, "mma_passes": passes,
+            # tensor-core time units per MAC: 3 fp16 products, or 1 fp16 + 2 e4m3 products at twice the rate
             "issued_frac": passes * achieved / peak, "traffic": traffic,
             "bare_conv": {"ms_per_launch": ms_planes, "achieved": flops / (ms_planes * 1e-3) / 1e12,
                           "frac": flops / (ms_planes * 1e-3) / 1e12 / peak,
