@@ -281,3 +281,22 @@ def test_fp8_correction_planes_and_scales_reproduce_the_product():
     err = float((got - ref).norm() / ref.norm())
     err_1pass = float((2.0 ** -k * main - ref).norm() / ref.norm())
     assert err < 2e-5 < 2e-4 < err_1pass, (err, err_1pass)
+
+
+def test_numerics_study_e4m3_emulator_matches_torch_float8():
+    """tools/numerics_study.py's e4m3 rounding (the evidence behind the 2-unit conv mode) is bit-identical to
+    torch.float8_e4m3fn on power-of-two-prescaled data, subnormals and saturation included."""
+    import importlib.util
+    import math
+    spec = importlib.util.spec_from_file_location("numerics_study", ROOT / "tools" / "numerics_study.py")
+    ns = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["numerics_study.py"]
+    try:
+        spec.loader.exec_module(ns)
+    finally:
+        sys.argv = argv
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(50000, generator=g, dtype=torch.float64) * torch.exp(2 * torch.randn(50000, generator=g, dtype=torch.float64))
+    k = math.floor(math.log2(448.0 / float(x.abs().max())))
+    ref = (x * 2.0 ** k).float().clamp(-448, 448).to(torch.float8_e4m3fn).double() * 2.0 ** -k
+    assert torch.equal(ns.e4m3(x), ref)
