@@ -15,6 +15,7 @@ Accumulation is float64 here, so this isolates OPERAND precision (the tensor cor
 accumulator adds 0.3e-6 ... 9e-6 per conv on top, see tests/test_ops_gpu.py).
 
     python tools/numerics_study.py [W=128] [t=0.6]      # a few minutes on 8 cores; writes nothing, prints a table
+    python tools/numerics_study.py --sampler            # per-step error of the PC sampler's updates (N = 30)
 """
 import sys
 from pathlib import Path
@@ -28,6 +29,9 @@ import torch.nn.functional as F  # noqa: E402
 
 from oracle import ncsnpp_ref as nr, weights as ow  # noqa: E402
 
+SAMPLER = "--sampler" in sys.argv
+if SAMPLER:
+    sys.argv.remove("--sampler")
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 torch.manual_seed(0)
 torch.set_num_threads(8)
@@ -139,5 +143,50 @@ def main():
         print(f"| {name} | {pol.hit} of {pol.calls} | {rel(out, truth):.2e} |", flush=True)
 
 
+def sampler_study(T=8000, N=30, steps=(0, 9, 19, 29)):
+    """Per-step view (the north-star criterion: per-step output within 1e-4 rel-L2): the reference's PC sampler
+    (reverse_diffusion + ald2, 1 corrector step, N = 30) runs in float64 with exact convolutions; at a few steps the
+    corrector and the predictor update are repeated FROM THE EXACT STATE with each operand scheme, and the state
+    they produce is compared with the exact one."""
+    from oracle import score_ref as sr, sde_ref as sd
+    import cases
+    params = {k: v.double() for k, v in ow.make_backbone_params(nf=128, seed=0).items()}
+    mix = sd.normalize_batch(cases.batch_mix(1, T).double())[0]
+    noises = [n.double() for n in cases.sampler_noises(1, T, N, 1)]
+    p = sd.MixSDEParams(N=N)
+    ts = sd.timesteps(p, 0.03, None, mix.dtype)
+
+    def score(policy):
+        def fn(x, t, m):
+            nr.F.conv2d = policy.conv if policy is not None else _real_conv2d
+            try:
+                with torch.no_grad():
+                    return sr.score_forward(params, x, t, m)
+            finally:
+                nr.F.conv2d = _real_conv2d
+        return fn
+    schemes = (("1 product", "1"), ("fp16 hi*hi + e4m3 corrections", "fp8corr"))
+    print(f"\nPC sampler N={N}, 1 corrector step, T={T}, float64: rel-L2 of ONE update from the exact state\n")
+    print("| step (t) | " + " | ".join(f"{n}: corrector | predictor" for n, _ in schemes) + " |")
+    print("|---|" + "---:|" * (2 * len(schemes)))
+    xt = sd.prior_sampling(p, mix, noises[0])
+    for i in range(N):
+        vec_t = torch.ones(1, dtype=mix.dtype) * ts[i]
+        zc, zp = noises[1 + 2 * i], noises[2 + 2 * i]
+        xc, _ = sd.corrector_step(p, score(None), xt, vec_t, mix, [zc], 0.5)
+        xp, _ = sd.predictor_step(p, score(None), xc, vec_t, mix, zp)
+        if i in steps:
+            cells = []
+            for _, mode in schemes:
+                gc, _ = sd.corrector_step(p, score(Policy(mode)), xt, vec_t, mix, [zc], 0.5)
+                gp, _ = sd.predictor_step(p, score(Policy(mode)), xc, vec_t, mix, zp)
+                cells += [f"{rel(gc, xc):.2e}", f"{rel(gp, xp):.2e}"]
+            print(f"| {i + 1} ({float(ts[i]):.2f}) | " + " | ".join(cells) + " |", flush=True)
+        xt = xp
+
+
 if __name__ == "__main__":
-    main()
+    if SAMPLER:
+        sampler_study()
+    else:
+        main()
