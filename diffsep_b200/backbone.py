@@ -397,8 +397,9 @@ class _Plan:
             s0, S0, s1, S1 = shortcut_raw
             kw = dict(s0=s0, S0=S0, s1=s1, S1=S1, Cin2=cw.cin2_pad, w2=cw.planes2)
         if net.passes == 2 and cw.cout_pad >= 64:      # experimental: fp16 hi*hi + one e4m3 correction product
+            w8 = cw.planes8()                          # built now, not inside a replayed / captured step
             self.steps.append(lambda: ops.conv2d_fused(
-                B, H, W, cin, cw.planes8(), cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1,
+                B, H, W, cin, w8, cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1,
                 sc=sc, sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=stride, residual=residual,
                 scale=scale, acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
                 a8_exp=cw.A8_EXP, **kw))
