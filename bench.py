@@ -60,7 +60,7 @@ def config_dict(n_gpus):
         "global_batch": B_PER_GPU * n_gpus, "samples": T, "n_fft": 510, "hop": 128, "N": N_STEPS,
         "corrector_steps": CORR_STEPS, "snr": SNR, "nf": NF, "sde": "PriorMixSDE" if PRIOR else "MixSDE",
         "predictor": "reverse_diffusion",
-        "corrector": "ald2", "passes": int(os.environ.get("DSEP_PASSES", "3")),
+        "corrector": "ald2", "passes": int(os.environ.get("DSEP_PASSES", "2")),
         "l2": "working set (>4 GB of activations per evaluation) exceeds the 126 MB L2; no flush needed",
         "parallelism": f"dp{n_gpus} (utterance sharding, one all-gather of outputs)",
     }
@@ -177,10 +177,10 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device()
-    passes = int(os.environ.get("DSEP_PASSES", "3"))
+    passes = int(os.environ.get("DSEP_PASSES", "2"))
     if passes not in (1, 2, 3):
-        raise SystemExit("DSEP_PASSES must be 3 (parity mode), 1 (TF32-grade) or 2 (experimental e4m3 corrections: "
-                         "needs DSEP_LIB = a -DDSEP_FP8_CORR=1 build of libdsep)")
+        raise SystemExit("DSEP_PASSES must be 2 (default: fp16 hi*hi + e4m3 corrections), 3 (three fp16 products) "
+                         "or 1 (TF32-grade, not a parity mode)")
 
     import copy
     cfg = copy.deepcopy(DEFAULT_CONFIG)

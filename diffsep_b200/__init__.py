@@ -2,7 +2,14 @@
 (fakufaku/diffusion-separation): STFT-510, NCSN++ score network, MixSDE predictor-corrector
 sampler, behind the reference's own Python surfaces.  All arithmetic runs in ``libdsep.so``
 (hand-written sm_100a kernels, C-ABI in ``include/dsep.h``); there is no CPU fallback."""
-__all__ = ["DiffSepModel", "ScoreModelNCSNpp", "sdes", "ops"]
+import os as _os
+
+__all__ = ["DiffSepModel", "ScoreModelNCSNpp", "sdes", "ops", "DEFAULT_PASSES"]
+
+# Tensor-core products per fp32-grade MAC of the convolutions (DESIGN.md §3): 2 = fp16 hi*hi + one e4m3 product
+# carrying both correction terms (the product default), 3 = three fp16 products, 1 = hi*hi only (TF32-grade, not
+# a parity mode).
+DEFAULT_PASSES = int(_os.environ.get("DSEP_PASSES", "2"))
 
 
 def __getattr__(name):

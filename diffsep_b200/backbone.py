@@ -97,7 +97,7 @@ class ConvWeight:
             self.bias = b
 
 
-    # ---- experimental passes = 2 (libdsep built with -DDSEP_FP8_CORR=1): e4m3 correction plane
+    # ---- passes = 2: e4m3 correction plane
     A8_EXP = 3            # activations enter the e4m3 planes as A_hi * 2^3 (saturating above 56) and A_lo * 2^14
     W8_EXP = -3           # fp16 weight planes hold |W * 2^k| < 2048: W_hi * 2^-3 < 256 and W_lo * 2^8 <= 128 fit e4m3
 
@@ -171,15 +171,17 @@ class Arena:
 class NCSNppB200:
     """The NCSN++ backbone: ``__call__(x_planes, x_pyramid, t) -> pyramid`` over a replayed plan."""
 
-    def __init__(self, params, nf=128, ch_in=6, ch_out=4, device="cuda", passes=3, fuse=None):
+    def __init__(self, params, nf=128, ch_in=6, ch_out=4, device="cuda", passes=None, fuse=None):
         ops.require_device()
         self.device = torch.device(device)
+        from . import DEFAULT_PASSES
+        passes = DEFAULT_PASSES if passes is None else int(passes)
         self.nf, self.ch_in, self.ch_out, self.passes = nf, ch_in, ch_out, passes
         if passes == 2:
             from . import _lib
             if not _lib.load().dsep_has_fp8_corr():
-                raise NotImplementedError("passes=2 (e4m3 correction products) needs libdsep built with "
-                                          "-DDSEP_FP8_CORR=1 (tools/build_variant.sh, DSEP_LIB)")
+                raise NotImplementedError("passes=2 (e4m3 correction products): this libdsep was built with "
+                                          "-DDSEP_FP8_CORR=0")
         # convs that still take operand planes (small maps, FIR-resampled inputs, narrow outputs) stay at 3 products
         self.plane_passes = 3 if passes == 2 else passes
         # in-kernel GroupNorm/SiLU/concat prologue (dsep_conv2d_fused) where shapes allow.  With three
@@ -361,13 +363,21 @@ class _Plan:
 
     # -- helpers that append launches ------------------------------------------------------
     def _conv(self, a, H, W, cin_pad, cw: ConvWeight, out, cout_store, film=None, residual=None, scale=1.0,
-              a2=None, stats=None):
+              a2=None, stats=None, e4m3=False):
+        """e4m3: ``a`` holds (fp16 hi, e4m3 correction) planes (fir_resample with a8_exp) -> passes = 2."""
         net, B = self.net, self.B
         film_v, stride = None, 0
         if film is not None:
             film_v, stride = self.film[:, film:], self.film.shape[1]
         w2 = cw.planes2 if a2 is not None else None
         cin2 = cw.cin2_pad if a2 is not None else 0
+        if e4m3:
+            w8 = cw.planes8()
+            self.steps.append(lambda: ops.conv2d_tc(
+                a, B, H, W, cin_pad, w8, cw.cout_pad, cw.ksize, out, cout_store, bias=cw.bias, film=film_v,
+                film_stride=stride, residual=residual, scale=scale, acc_scale=cw.acc_scale, passes=2, a2=a2,
+                Cin2=cin2, w2=w2, stats=stats, corr_rel=cw.corr_rel, a8_exp=cw.A8_EXP))
+            return
         self.steps.append(lambda: ops.conv2d_tc(
             a() if callable(a) else a, B, H, W, cin_pad, cw.planes, cw.cout_pad, cw.ksize, out, cout_store,
             bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
@@ -396,7 +406,7 @@ class _Plan:
         if shortcut_raw is not None:
             s0, S0, s1, S1 = shortcut_raw
             kw = dict(s0=s0, S0=S0, s1=s1, S1=S1, Cin2=cw.cin2_pad, w2=cw.planes2)
-        if net.passes == 2 and cw.cout_pad >= 64:      # experimental: fp16 hi*hi + one e4m3 correction product
+        if net.passes == 2 and cw.cout_pad >= 64:      # fp16 hi*hi + one e4m3 product for both correction terms
             w8 = cw.planes8()                          # built now, not inside a replayed / captured step
             self.steps.append(lambda: ops.conv2d_fused(
                 B, H, W, cin, w8, cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1,
@@ -456,9 +466,11 @@ class _Plan:
             # shortcut in-kernel (all of a launch's A patches come from ONE agent: TMA or workers)
             assert mode != 0 and x1 is None and rb["has_shortcut"]
             xr = ar.f32(B, Ho, Wo, Cin)
+            e4 = self.net.passes == 2 and rb["conv0"].cout_pad >= 64
+            a8 = ConvWeight.A8_EXP if e4 else None
             self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
-                                                       a=a, y=xr))
-            self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st)
+                                                       a=a, y=xr, a8_exp=a8))
+            self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st, e4m3=e4)
             ar.release(a)
             st_h = self._ensure_stats(h)
             sc1, sh1 = self._tables(st_h, Cout, None, 0, Ho * Wo, gam1, bet1)

@@ -41,6 +41,16 @@
 
 #include "common.cuh"
 
+// passes = 2 (the product default; -DDSEP_FP8_CORR=0 compiles it out): per K=16 step ONE fp16 product hi*hi plus
+// ONE e4m3 tensor-core product that carries both correction terms, [A_lo8 | A_hi8] x [W_hi8 ; W_lo8] (K = 32
+// bytes, twice the fp16 rate) = 2 tensor-core units per MAC instead of 3.  tools/numerics_study.py: network error
+// 4.7e-5 from the operand rounding (budget 1e-4; dropping either correction in a single level-0 conv costs
+// 2.4e-4).  Halo kernel only (maps of at least 16 x 8, Cout >= 64); the main operand is either built in-kernel
+// or arrives as (fp16 hi, e4m3 correction) planes by TMA (dsep_fir_resample8 writes them).
+#ifndef DSEP_FP8_CORR
+#define DSEP_FP8_CORR 1
+#endif
+
 namespace dsep {
 
 struct ConvParams {
@@ -78,15 +88,6 @@ constexpr int kThreads = 128 + kEpiWarps * 32;
 // delivery (~12.6 TB/s with 128-byte rows, ~7 TB/s with 64-byte rows), not by ring depth.
 #ifndef DSEP_CONV_BK
 #define DSEP_CONV_BK 64
-#endif
-// Build switch (off: the shipped binary does not contain this path).  1 adds passes = 2 to the halo kernel with
-// in-kernel prologue: per K=16 step ONE fp16 product hi*hi plus ONE e4m3 tensor-core product that carries both
-// correction terms, [A_lo8 | A_hi8] x [W_hi8 ; W_lo8] (K = 32 bytes, twice the fp16 rate) = 2 tensor-core units
-// per MAC instead of 3.  tools/numerics_study.py: network error 4.7e-5 from the operand rounding (budget 1e-4;
-// dropping either correction in a single level-0 conv costs 2.4e-4).  First hardware run: op-level parity tests
-// pass (< 3e-5 vs float64), level-0 conv 1.34 ms vs 1.40-1.42 ms; not yet validated at network level.
-#ifndef DSEP_FP8_CORR
-#define DSEP_FP8_CORR 0
 #endif
 constexpr int kBK = DSEP_CONV_BK;
 static_assert(kBK == 32 || kBK == 64, "K-block must be 32 or 64 channels");
@@ -1179,8 +1180,8 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
     DSEP_REQUIRE((g->a_hi || main_fused) && g->w_hi && g->out, "conv2d_tc: null operand");
 #if DSEP_FP8_CORR
     DSEP_REQUIRE(passes == 1 || passes == 2 || passes == 3, "conv2d_tc: passes must be 1, 2 or 3 (got %d)", passes);
-    DSEP_REQUIRE(passes != 2 || (main_fused && Cout_pad % 64 == 0 && H >= 16 && W >= 8 && corr_rel > 0.f),
-                 "conv2d_fused8: e4m3 corrections need the in-kernel prologue, Cout >= 64 and a map of at least 16 x 8");
+    DSEP_REQUIRE(passes != 2 || (kBK == 64 && Cout_pad % 64 == 0 && H >= 16 && W >= 8 && corr_rel > 0.f),
+                 "conv2d_fused8: e4m3 corrections need Cout >= 64 and a map of at least 16 x 8");
 #else
     DSEP_REQUIRE(passes == 1 || passes == 3, "conv2d_tc: passes must be 1 or 3 (got %d)", passes);
     (void)corr_rel; (void)a8_exp;
@@ -1208,7 +1209,7 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
     static const int halo_env = getenv("DSEP_CONV_HALO") ? atoi(getenv("DSEP_CONV_HALO")) : 1;
     // narrow outputs (Cout_pad = 16: the pyramid convs) take the halo kernel only with the in-kernel prologue
     const bool halo_ok = kBK == 64 && W >= 8 && H >= 16 && (Cout_pad != 16 || (main_fused && Cin2 == 0));
-    const bool halo = halo_ok && (main_fused || short_fused || (halo_env != 0 && ksize == 3));
+    const bool halo = halo_ok && (main_fused || short_fused || passes == 2 || (halo_env != 0 && ksize == 3));
     DSEP_REQUIRE(!(main_fused || short_fused) || halo_ok,
                  "conv2d_fused: the in-kernel prologue needs a map of at least 16 x 8 (and no fused shortcut when "
                  "Cout_pad is 16; got %dx%d, Cout_pad %d)", H, W, Cout_pad);

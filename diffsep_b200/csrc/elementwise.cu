@@ -36,6 +36,28 @@ __device__ __forceinline__ void split4(const float4 x, f16x4& hi, f16x4& lo) {
     split_f16(x.w, hi.v[3], lo.v[3]);
 }
 
+// (hi fp16, e4m3 correction) form of a quad for the convolution's passes = 2 mode: per 8 channels the second
+// plane holds the 16 bytes [A_lo8 x 8 | A_hi8 x 8] (conv_tc.cu patch_store); this quad's channels are
+// 4 * (q & 1) .. + 3 of its group of 8.  a8_hi / a8_lo are the power-of-two prescales of the two parts.
+__device__ __forceinline__ uint32_t e4m3x4_pack(float a, float b, float c, float d) {
+    uint16_t p0, p1;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p0) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p1) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(p0) | (static_cast<uint32_t>(p1) << 16);
+}
+__device__ __forceinline__ void split4_e4m3(const float4 x, f16x4& hi, uint32_t& lo8, uint32_t& hi8, float a8_hi,
+                                            float a8_lo) {
+    f16x4 l;
+    split4(x, hi, l);
+    const float h0 = __half2float(hi.v[0]), h1 = __half2float(hi.v[1]), h2 = __half2float(hi.v[2]),
+                h3 = __half2float(hi.v[3]);
+    const float c = 60000.0f;      // split_f16 clamps before rounding; take the residual of the clamped value
+    const float x0 = fminf(fmaxf(x.x, -c), c), x1 = fminf(fmaxf(x.y, -c), c), x2 = fminf(fmaxf(x.z, -c), c),
+                x3 = fminf(fmaxf(x.w, -c), c);
+    lo8 = e4m3x4_pack((x0 - h0) * a8_lo, (x1 - h1) * a8_lo, (x2 - h2) * a8_lo, (x3 - h3) * a8_lo);
+    hi8 = e4m3x4_pack(h0 * a8_hi, h1 * a8_hi, h2 * a8_hi, h3 * a8_hi);
+}
+
 // ---------------------------------------------------------------------------- split
 __global__ void split_kernel(const float* __restrict__ x, int64_t n4, float prescale,
                              f16x4* __restrict__ hi, f16x4* __restrict__ lo) {
@@ -223,7 +245,8 @@ __global__ void __launch_bounds__(256)
 fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, const double* __restrict__ st,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
-                f16x4* __restrict__ r_lo, float4* __restrict__ y, int tiles_w, int tiles_h) {
+                f16x4* __restrict__ r_lo, float4* __restrict__ y, int tiles_w, int tiles_h, float a8_hi,
+                float a8_lo) {
     using FT = FirTile<MODE>;
     extern __shared__ __align__(16) float s_fir[];
     float4* s_act = reinterpret_cast<float4*>(s_fir);                  // [IH*IW][8 quads]
@@ -325,7 +348,18 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
         }
         const size_t o = ((static_cast<size_t>(b) * Ho + oh) * Wo + ow) * Q + chunk * 8 + q;
         f16x4 h, l;
-        if (a_hi != nullptr) { split4(acc_a, h, l); a_hi[o] = h; a_lo[o] = l; }
+        if (a_hi != nullptr) {
+            if (a8_hi != 0.f) {      // second plane = e4m3 corrections: [A_lo8 x 8 | A_hi8 x 8] per 8 channels
+                uint32_t lo8, hi8;
+                split4_e4m3(acc_a, h, lo8, hi8, a8_hi, a8_lo);
+                a_hi[o] = h;
+                uint32_t* g8 = reinterpret_cast<uint32_t*>(a_lo + (o & ~static_cast<size_t>(1)));   // the group's 16 bytes
+                g8[o & 1] = lo8;
+                g8[2 + (o & 1)] = hi8;
+            } else {
+                split4(acc_a, h, l); a_hi[o] = h; a_lo[o] = l;
+            }
+        }
         if (r_hi != nullptr) { split4(acc_r, h, l); r_hi[o] = h; r_lo[o] = l; }
         if (y != nullptr) y[o] = acc_r;
     }
@@ -517,7 +551,7 @@ extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, con
 template <int MODE>
 static int launch_fir_tile(const float* x, int B, int H, int W, int C, int groups, const double* st,
                            const float* gamma, const float* beta, float eps, void* a_hi, void* a_lo,
-                           void* r_hi, void* r_lo, float* y, cudaStream_t s) {
+                           void* r_hi, void* r_lo, float* y, float a8_hi, float a8_lo, cudaStream_t s) {
     using FT = FirTile<MODE>;
     static bool configured = false;
     if (!configured) {
@@ -534,14 +568,14 @@ static int launch_fir_tile(const float* x, int B, int H, int W, int C, int group
     dim3 grid(tiles_w * tiles_h, C / 32, B);
     fir_tile_kernel<MODE><<<grid, 256, FT::kSmemBytes, s>>>(x, H, W, C, groups, st, gamma, beta, eps, (f16x4*)a_hi,
                                                             (f16x4*)a_lo, (f16x4*)r_hi, (f16x4*)r_lo, (float4*)y,
-                                                            tiles_w, tiles_h);
+                                                            tiles_w, tiles_h, a8_hi, a8_lo);
     return check_launch("fir_tile_kernel");
 }
 
-extern "C" int dsep_fir_resample(const float* x, int B, int H, int W, int C, int mode, int groups,
-                                 const double* st, const float* gamma, const float* beta, float eps,
-                                 void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y,
-                                 dsep_stream_t stream) {
+static int fir_resample_impl(const float* x, int B, int H, int W, int C, int mode, int groups,
+                             const double* st, const float* gamma, const float* beta, float eps,
+                             void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y, float a8_hi, float a8_lo,
+                             dsep_stream_t stream) {
     DSEP_REQUIRE(x, "fir_resample: null input");
     DSEP_REQUIRE(mode == 1 || mode == 2, "fir_resample: mode must be 1 (up) or 2 (down)");
     DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && B <= 65535, "fir_resample: empty tensor");
@@ -563,8 +597,28 @@ extern "C" int dsep_fir_resample(const float* x, int B, int H, int W, int C, int
         int rc = check_gn_shape("fir_resample", C, 0, groups);
         if (rc) return rc;
     }
-    return mode == 1 ? launch_fir_tile<1>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, s)
-                     : launch_fir_tile<2>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, s);
+    return mode == 1 ? launch_fir_tile<1>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y,
+                                          a8_hi, a8_lo, s)
+                     : launch_fir_tile<2>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y,
+                                          a8_hi, a8_lo, s);
+}
+
+extern "C" int dsep_fir_resample(const float* x, int B, int H, int W, int C, int mode, int groups,
+                                 const double* st, const float* gamma, const float* beta, float eps,
+                                 void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y,
+                                 dsep_stream_t stream) {
+    return fir_resample_impl(x, B, H, W, C, mode, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, 0.f, 0.f,
+                             stream);
+}
+
+extern "C" int dsep_fir_resample8(const float* x, int B, int H, int W, int C, int mode, int groups,
+                                  const double* st, const float* gamma, const float* beta, float eps,
+                                  void* a_hi, void* a_8, void* r_hi, void* r_lo, float* y, int a8_exp,
+                                  dsep_stream_t stream) {
+    DSEP_REQUIRE(a_hi && a_8 && C % 32 == 0, "fir_resample8: needs the a planes and C %% 32 == 0");
+    DSEP_REQUIRE(a8_exp >= -8 && a8_exp <= 8, "fir_resample8: a8_exp out of range");
+    return fir_resample_impl(x, B, H, W, C, mode, groups, st, gamma, beta, eps, a_hi, a_8, r_hi, r_lo, y,
+                             ldexpf(1.0f, a8_exp), ldexpf(1.0f, a8_exp + 11), stream);
 }
 
 extern "C" int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_x, int up_y, int down_x,

@@ -70,10 +70,15 @@ def split_f16(x, out: Split, prescale=1.0):
 
 def conv2d_tc(a: Split, B, H, W, Cin, w: Split, cout_pad, ksize, out, cout_store, bias=None, film=None,
               film_stride=0, residual=None, scale=1.0, acc_scale=1.0, passes=3, a2: Split = None, Cin2=0,
-              w2: Split = None, stats=None):
+              w2: Split = None, stats=None, corr_rel=1.0, a8_exp=0):
+    """passes = 2: ``a.lo`` / ``w.lo`` are the e4m3 correction planes (dsep_conv2d_fused8 fed with planes)."""
     _f32(out, "out"); _f32(bias, "bias"); _f32(film, "film"); _f32(residual, "residual")
     if stats is not None and stats.dtype != torch.float64:
         raise ValueError("stats must be float64 [B, C, 2]")
+    if passes == 2:
+        return conv2d_fused(B, H, W, Cin, w, cout_pad, ksize, out, cout_store, a=a, a2=a2, Cin2=Cin2, w2=w2, bias=bias,
+                            film=film, film_stride=film_stride, residual=residual, scale=scale, acc_scale=acc_scale,
+                            stats=stats, passes=2, corr_rel=corr_rel, a8_exp=a8_exp)
     call("dsep_conv2d_tc", ptr(a.hi), ptr(a.lo), B, H, W, Cin, ptr(w.hi), ptr(w.lo), cout_pad, ksize,
          ptr(a2.hi) if a2 else None, ptr(a2.lo) if a2 else None, Cin2, ptr(w2.hi) if w2 else None,
          ptr(w2.lo) if w2 else None, ptr(bias), film.data_ptr() if film is not None else None, film_stride,
@@ -134,7 +139,12 @@ def gn_act_split(x0, C0, st0, x1, C1, st1, B, P, groups, gamma, beta, eps, act, 
 
 
 def fir_resample(x, B, H, W, Cc, mode, groups=0, stats=None, gamma=None, beta=None, eps=1e-6, a: Split = None,
-                 r: Split = None, y=None):
+                 r: Split = None, y=None, a8_exp=None):
+    """a8_exp given: ``a.lo`` receives the e4m3 correction plane of the passes = 2 convolution instead of fp16 lo."""
+    if a8_exp is not None:
+        call("dsep_fir_resample8", ptr(_f32(x, "x")), B, H, W, Cc, mode, groups, ptr(stats), ptr(gamma), ptr(beta),
+             eps, ptr(a.hi), ptr(a.lo), ptr(r.hi) if r else None, ptr(r.lo) if r else None, ptr(y), a8_exp, stream())
+        return
     call("dsep_fir_resample", ptr(_f32(x, "x")), B, H, W, Cc, mode, groups, ptr(stats), ptr(gamma), ptr(beta),
          eps, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
          ptr(r.lo) if r else None, ptr(y), stream())

@@ -103,7 +103,7 @@ DEFAULT_CONFIG = {   # reference config/model/default.yaml + experiment/icassp-s
 
 
 class DiffSepModel(torch.nn.Module):
-    def __init__(self, config=None, device="cuda", passes=3, score_state_dict=None):
+    def __init__(self, config=None, device="cuda", passes=None, score_state_dict=None):
         super().__init__()
         cfg = _to_plain(config) if config is not None else DEFAULT_CONFIG
         self.config = _ns(cfg)
@@ -171,7 +171,7 @@ class DiffSepModel(torch.nn.Module):
 
     # ------------------------------------------------------------------ checkpoints
     @classmethod
-    def load_from_checkpoint(cls, path, map_location=None, device="cuda", passes=3, **kwargs):
+    def load_from_checkpoint(cls, path, map_location=None, device="cuda", passes=None, **kwargs):
         """Reads a Lightning ``.ckpt`` / HF ``checkpoint.pt``: ``hyper_parameters.config``,
         ``state_dict`` (``score_model.*``), and — because the reference swaps EMA weights in on
         ``.eval()`` (pl_model.py:650-670) — ``ema.shadow_params`` in ``parameters()`` order."""

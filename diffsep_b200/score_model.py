@@ -60,7 +60,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
 
     def __init__(self, num_sources=2, stft_args=None, backbone_args=None, transform="exponent",
                  spec_abs_exponent=0.5, spec_factor=0.15, spec_trans_learnable=False,
-                 state_dict=None, device="cuda", passes=3, **kwargs):
+                 state_dict=None, device="cuda", passes=None, **kwargs):
         super().__init__()
         stft_args = dict(stft_args or dict(n_fft=510, hop_length=128, center=True, pad_mode="constant"))
         if stft_args.get("n_fft", 510) != 510 or stft_args.get("hop_length", 128) != 128:
@@ -85,7 +85,8 @@ class ScoreModelNCSNpp(torch.nn.Module):
             if unsupported:
                 raise NotImplementedError(f"backbone options outside the hot path: {unsupported}")
         self.dev = torch.device(device)
-        self.passes = passes
+        from . import DEFAULT_PASSES
+        self.passes = DEFAULT_PASSES if passes is None else int(passes)
         self.ch_in = 2 * num_sources + 2
         self.ch_out = 2 * num_sources
         self.backbone = None

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 5
+#define DSEP_ABI_VERSION 6
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -39,7 +39,7 @@ const char* dsep_last_error(void);
 int dsep_abi_version(void);
 /* 1 if the running device is sm_100 (B200); the product path refuses anything else. */
 int dsep_device_ok(void);
-/* channel granularity of dsep_conv2d_tc's operands (Cin, Cin2 must be multiples of it): 32 */
+/* channel granularity of dsep_conv2d_tc's operands (Cin, Cin2 must be multiples of it): 64 */
 int dsep_conv_kblock(void);
 
 /* ---- tensor-core convolution -------------------------------------------------------------
@@ -101,14 +101,16 @@ typedef struct {
     int passes;
 } dsep_conv_args;
 int dsep_conv2d_fused(const dsep_conv_args* args, dsep_stream_t stream);
-/* Experimental build switch -DDSEP_FP8_CORR=1 (dsep_has_fp8_corr() == 1; off in the shipped binary, where this
- * entry point returns DSEP_ERR_UNSUPPORTED): the same fused convolution with passes = 2 — per K = 16 step one fp16
- * product hi*hi plus ONE e4m3 tensor-core product carrying both correction terms (2 tensor-core units per MAC
- * instead of 3; tools/numerics_study.py).  args->w_lo then points to the e4m3 weight plane [taps, Cout_pad, 2*Cin]
- * bytes: per 8 input channels the 16 bytes [W_hi8 x 8 | W_lo8 x 8], W_hi8 = e4m3(W_hi * 2^q), W_lo8 =
- * e4m3(W_lo * 2^(q+11)) on top of the fp16 planes' prescale; activations are prescaled in-kernel by 2^a8_exp
- * (hi) and 2^(a8_exp+11) (lo); corr_rel = 2^-(q + a8_exp + 11) weighs the correction accumulator.  A fused 1x1
- * shortcut keeps fp16 (hi, lo) planes.  Needs x0 (in-kernel prologue), Cout >= 64, a map of at least 16 x 8. */
+/* The product's default mode, passes = 2 (dsep_has_fp8_corr() == 1 unless built with -DDSEP_FP8_CORR=0, where this
+ * entry point returns DSEP_ERR_UNSUPPORTED): the same convolution with per K = 16 step one fp16 product hi*hi plus
+ * ONE e4m3 tensor-core product carrying both correction terms (2 tensor-core units per MAC instead of 3;
+ * tools/numerics_study.py, profiles/parity_r02.md).  args->w_lo then points to the e4m3 weight plane
+ * [taps, Cout_pad, 2*Cin] bytes: per 8 input channels the 16 bytes [W_hi8 x 8 | W_lo8 x 8], W_hi8 = e4m3(W_hi * 2^q),
+ * W_lo8 = e4m3(W_lo * 2^(q+11)) on top of the fp16 planes' prescale; activations are prescaled by 2^a8_exp (hi) and
+ * 2^(a8_exp+11) (lo) — in-kernel when x0 is given, otherwise a_lo must already be the e4m3 activation plane
+ * [B,H,W,2*Cin] bytes, per 8 channels [A_lo8 x 8 | A_hi8 x 8] (dsep_fir_resample8 writes it); corr_rel =
+ * 2^-(q + a8_exp + 11) weighs the correction accumulator.  A fused 1x1 shortcut keeps fp16 (hi, lo) planes.
+ * Needs Cout >= 64 and a map of at least 16 x 8 (the halo kernel). */
 int dsep_conv2d_fused8(const dsep_conv_args* args, float corr_rel, int a8_exp, dsep_stream_t stream);
 int dsep_has_fp8_corr(void);
 /* Per-(batch entry, channel) GroupNorm scale / shift from per-channel sums of a (concatenated) input:
@@ -146,6 +148,12 @@ int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x
 int dsep_fir_resample(const float* x, int B, int H, int W, int C, int mode, int groups,
                       const double* st, const float* gamma, const float* beta, float eps,
                       void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y, dsep_stream_t stream);
+/* Same, with the a operand written for dsep_conv2d_fused8: a_hi = fp16 hi plane, a_8 = the e4m3 correction plane
+ * ([B,Ho,Wo,2*C] bytes: per 8 channels [A_lo8 x 8 | A_hi8 x 8], prescaled by 2^(a8_exp+11) / 2^a8_exp). */
+int dsep_fir_resample8(const float* x, int B, int H, int W, int C, int mode, int groups,
+                       const double* st, const float* gamma, const float* beta, float eps,
+                       void* a_hi, void* a_8, void* r_hi, void* r_lo, float* y, int a8_exp,
+                       dsep_stream_t stream);
 /* Drop-in for the reference's own FFI signature on its own layout: in [planes, H, W] fp32,
  * kernel fixed to outer([1,3,3,1])/16*up^2; supports exactly the two calls the model makes
  * (up=2,down=1,pad=(2,1)) and (up=1,down=2,pad=(1,1)); anything else -> DSEP_ERR_UNSUPPORTED.

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS)
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_abi_argument_counts_match_header():
@@ -231,19 +231,23 @@ def test_checkpoint_state_swaps_ema_weights_in():
         checkpoint_state(dict(ckpt, ema={"shadow_params": shadow}))
 
 
-def test_fp8_correction_entry_point_is_gated(lib):
-    """The experimental e4m3-correction mode is a build switch: the shipped library exports the entry point but
-    answers DSEP_ERR_UNSUPPORTED (-> NotImplementedError), and the regular entry point rejects passes = 2."""
+def test_fp8_correction_entry_point_is_shipped_and_validates(lib):
+    """The e4m3-correction mode (passes = 2, the product default) is in the shipped library; its entry point
+    validates its arguments on the host before any launch, and the regular entry point rejects passes = 2."""
     import ctypes as C
+    import diffsep_b200
     from diffsep_b200 import _lib
-    if lib.dsep_has_fp8_corr():
-        pytest.skip("this libdsep has the e4m3-correction mode")
+    assert lib.dsep_has_fp8_corr() == 1
+    assert diffsep_b200.DEFAULT_PASSES in (1, 2, 3)
     g = _lib.ConvArgs()
     g.passes = 2
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):          # null operands
         _lib.call("dsep_conv2d_fused8", C.byref(g), 2.0 ** -11, 3, None)
     with pytest.raises(ValueError):
         _lib.call("dsep_conv2d_fused", C.byref(g), None)
+    g.passes = 3
+    with pytest.raises(ValueError):          # fused8 is passes = 2 only
+        _lib.call("dsep_conv2d_fused8", C.byref(g), 2.0 ** -11, 3, None)
 
 
 def test_fp8_correction_planes_and_scales_reproduce_the_product():

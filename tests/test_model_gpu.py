@@ -274,12 +274,9 @@ def test_score_model_tf32_grade_mode():
 
 
 def test_score_model_e4m3_correction_mode_matches_reference_golden(golden):
-    """passes=2 (experimental build switch -DDSEP_FP8_CORR=1; skipped on the shipped library): fp16 hi*hi plus one
-    e4m3 product for both correction terms in every fused conv — two tensor-core units per MAC — still meets the
-    north-star tolerance against the real reference's golden (tools/numerics_study.py predicts ~5e-5)."""
-    from diffsep_b200 import _lib
-    if not _lib.load().dsep_has_fp8_corr():
-        pytest.skip("needs libdsep built with -DDSEP_FP8_CORR=1 (tools/build_variant.sh, DSEP_LIB)")
+    """passes=2 (the product default): fp16 hi*hi plus one e4m3 product for both correction terms in every conv on
+    a map of at least 16 x 8 — two tensor-core units per MAC — meets the north-star tolerance against the real
+    reference's golden (tools/numerics_study.py predicts ~5e-5)."""
     g = golden("score_nf128.npz")
     sm = _score_model(128, passes=2)
     xt, t, mix = cases.score_inputs(1, 7680, seed=9)

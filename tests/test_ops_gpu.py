@@ -269,18 +269,11 @@ def test_conv2d_fused_narrow_output(shape):
     assert rel_l2(nchw(out), ref) < 1e-5
 
 
-def _needs_fp8_corr():
-    from diffsep_b200 import _lib
-    if not _lib.load().dsep_has_fp8_corr():
-        pytest.skip("experimental e4m3-correction mode: needs libdsep built with -DDSEP_FP8_CORR=1 (DSEP_LIB)")
-
-
 @pytest.mark.parametrize("shape", [(2, 32, 24, 128, 128, 0), (1, 16, 40, 64, 128, 64), (1, 48, 16, 256, 64, 0)])
 def test_conv2d_fused8_e4m3_corrections(shape):
     """passes = 2: conv3x3(SiLU(GN(x))) [+ fp16 1x1 shortcut] with hi*hi in fp16 and both correction terms in ONE
     e4m3 tensor-core product, vs float64.  Operand error: the corrections (2^-11 of the result) carry 4
     significand bits -> ~2^-16 per term; tolerance 3e-5 per conv (tools/numerics_study.py: 4.7e-5 over the net)."""
-    _needs_fp8_corr()
     ops = _ops()
     from diffsep_b200.backbone import ConvWeight
     B, H, W, Cin, Cout, Cs = shape
@@ -319,16 +312,51 @@ def test_conv2d_fused8_e4m3_corrections(shape):
     assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
 
 
-def test_conv2d_fused8_unsupported_on_the_shipped_build():
-    from diffsep_b200 import _lib
-    if _lib.load().dsep_has_fp8_corr():
-        pytest.skip("this libdsep has the e4m3-correction mode")
+@pytest.mark.parametrize("shape", [(2, 16, 12, 128, 128, 1), (1, 64, 32, 128, 256, 2), (1, 32, 16, 256, 128, 2)])
+def test_conv2d_e4m3_corrections_from_fir_planes(shape):
+    """The up / down ResBlocks' Conv_0 in passes = 2: dsep_fir_resample8 writes FIR(SiLU(GN(x))) as (fp16 hi,
+    e4m3 correction) planes, the halo kernel takes them by TMA.  vs float64 (FIR restated with F.conv2d /
+    zero-stuffing as in up_or_down_sampling.py:206-273)."""
     ops = _ops()
-    w = ops.Split.zeros((9, 64, 64), DEV)
-    x = torch.zeros(1, 16, 8, 64, device=DEV)
-    with pytest.raises(NotImplementedError):
-        ops.conv2d_fused(1, 16, 8, 64, w, 64, 3, torch.empty(1, 16, 8, 64, device=DEV), 64, x0=x, C0=64, passes=2,
-                         corr_rel=2.0 ** -11, a8_exp=3)
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, C, Cout, mode = shape
+    g = cases.gen(sum(shape) + 11)
+    x = torch.randn(B, C, H, W, generator=g) * 1.1 - 0.05
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    w = torch.randn(Cout, C, 3, 3, generator=g) / math.sqrt(C * 9)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    a = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    a = a * torch.sigmoid(a)
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    k2 = torch.outer(k1, k1)
+    k2 = k2 / k2.sum()
+    if mode == 2:        # down: pad (1,1), stride 2
+        fa = F.conv2d(F.pad(a, (1, 1, 1, 1)).reshape(B * C, 1, H + 2, W + 2), k2[None, None], stride=2)
+        Ho, Wo = H // 2, W // 2
+    else:                # up: zero-stuff, pad (2,1), gain 4
+        z = torch.zeros(B * C, 1, 2 * H, 2 * W, dtype=torch.float64)
+        z[:, :, ::2, ::2] = a.reshape(B * C, 1, H, W)
+        fa = F.conv2d(F.pad(z, (2, 1, 2, 1)), (k2 * 4).flip(0, 1)[None, None])
+        Ho, Wo = 2 * H, 2 * W
+    fa = fa.reshape(B, C, Ho, Wo)
+    ref = F.conv2d(fa, w.double(), b1.double(), padding=1)
+    cw = ConvWeight(w, b1, DEV)
+    d0 = cl(x)
+    st0 = torch.empty(B, C, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, C, B, H * W, st0)
+    planes = ops.Split.empty((B, Ho, Wo, C), DEV)
+    y = torch.empty(B, Ho, Wo, C, device=DEV)
+    ops.fir_resample(d0, B, H, W, C, mode, 32, st0, gamma.to(DEV), beta.to(DEV), 1e-6, a=planes, y=y,
+                     a8_exp=cw.A8_EXP)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV)
+    stats = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    ops.conv2d_tc(planes, B, Ho, Wo, C, cw.planes8(), cw.cout_pad, 3, out, Cout, bias=cw.bias,
+                  acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel, a8_exp=cw.A8_EXP)
+    torch.cuda.synchronize()
+    assert rel_l2(planes.hi.float().permute(0, 3, 1, 2).cpu(), fa) < 1e-3      # the hi plane alone: 11 bits
+    assert rel_l2(nchw(out), ref) < 3e-5
+    assert rel_l2(stats[..., 0].cpu(), nchw(out).double().sum(dim=(2, 3))) < 1e-6
 
 
 def test_conv2d_fused_rejects_small_maps():

@@ -29,7 +29,7 @@ def rel(a, b):
     return float((a - b).norm() / b.norm())
 
 
-PASSES = int(__import__("os").environ.get("DSEP_PASSES", "3"))     # 2: the e4m3-correction variant (DSEP_LIB)
+PASSES = int(__import__("os").environ.get("DSEP_PASSES", "2"))     # 2: the e4m3-correction variant (DSEP_LIB)
 model = DiffSepModel(DEFAULT_CONFIG, passes=PASSES, score_state_dict=ow.make_score_model_state_dict(nf=NF, seed=0))
 params = ow.make_backbone_params(nf=NF, seed=0)
 mix_cpu, _, _ = sd.normalize_batch(cases.batch_mix(1, T))

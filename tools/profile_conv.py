@@ -22,7 +22,7 @@ H = W = int(os.environ.get("DSEP_HW", "256"))
 CIN = int(os.environ.get("DSEP_CIN", "128"))
 COUT = int(os.environ.get("DSEP_COUT", "128"))
 K = int(os.environ.get("DSEP_K", "3"))
-passes = int(os.environ.get("DSEP_PASSES", "3"))
+passes = int(os.environ.get("DSEP_PASSES", "2"))
 with_res = int(os.environ.get("DSEP_RES", "0"))
 reps = int(os.environ.get("DSEP_REPS", "5"))
 dev = "cuda"

@@ -21,7 +21,7 @@ from diffsep_b200 import synthetic as ow  # noqa: E402
 B = int(os.environ.get("DSEP_BENCH_BATCH", "32"))
 NF = int(os.environ.get("DSEP_NF", "128"))
 T = int(os.environ.get("DSEP_T", "32000"))
-passes = int(os.environ.get("DSEP_PASSES", "3"))
+passes = int(os.environ.get("DSEP_PASSES", "2"))
 sm = ScoreModelNCSNpp(num_sources=2, backbone_args=dict(nf=NF), passes=passes,
                       state_dict=ow.make_score_model_state_dict(nf=NF, seed=0))
 xt, t, mix = (v.cuda() for v in cases.score_inputs(B, T, seed=3))
