@@ -446,6 +446,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     // B rows are split between the CTAs.  X (NT rows): W_hi in the leader, W_lo in the
                     // follower = the two halves of the stacked [W_hi ; W_lo]; Y (NT/2 rows): this CTA's
                     // half of W_hi for the A_lo x W_hi product.  Everything completes on the leader's barrier.
+#if DSEP_FP8_CORR
+                    if (fp8c) {
+                        // each CTA holds its half of the rows of both weight planes (fp16 hi; e4m3 corrections, or
+                        // the fp16 lo plane of a shortcut K-block): N = NT products only
+                        if (rank == 0) mbar_arrive_expect_tx(&full[bs], 2u * HCfg::kBBytes);
+                        const int wr = wrow + static_cast<int>(rank) * (NT / 2);
+                        tma_load_2d_2sm(sb, whi, &full[bs], kcol, wr);
+                        tma_load_2d_2sm(sb + HCfg::kBBytes, wlo, &full[bs], kcol, wr);
+                        if (++bs == NS) { bs = 0; bph ^= 1u; }
+                        return;
+                    }
+#endif
                     if (rank == 0)
                         mbar_arrive_expect_tx(&full[bs], three ? 3u * HCfg::kBBytes : 1u * HCfg::kBBytes);
                     if (three) {
@@ -543,6 +555,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     if constexpr (TWO) umma_f16_2cta(d, a, b, idesc, acc_flag);
                     else umma_f16(d, a, b, idesc, acc_flag);
                 };
+#if DSEP_FP8_CORR
+                auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_flag) {
+                    if constexpr (TWO) umma_e4m3_2cta(d, a, b, idesc, acc_flag);
+                    else umma_e4m3(d, a, b, idesc, acc_flag);
+                };
+#endif
                 auto commit_pair = [&](uint64_t* bar) {      // arrive in BOTH CTAs when the MMAs so far retire
                     if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
                     else umma_commit_mc(bar, 0x3);
@@ -585,7 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                                         const uint64_t b_2 = desc(b_word + (HCfg::kBBytes >> 4) + 2 * k, kHiPlain);
                                         mma(d_tmem, a_hi, b_hi, idesc_n, accumulate);              // hi*hi -> [0, NT)
                                         if (main_kb) {     // [A_lo8 | A_hi8] x [W_hi8 ; W_lo8], K = 32 -> [NT, 2NT)
-                                            umma_e4m3(d_tmem + NT, a_2, b_2, idesc_n, accumulate8);
+                                            mma8(d_tmem + NT, a_2, b_2, idesc_n, accumulate8);
                                             accumulate8 = 1;
                                         } else {           // fp16 shortcut K-block: all three products into [0, NT)
                                             mma(d_tmem, a_hi, b_2, idesc_n, 1);
@@ -1311,6 +1329,8 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
     static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
     if (halo && NT == 16) return launch_conv<16, true>(m, p, s);
 #if DSEP_FP8_CORR
+    if (passes == 2 && two_env)
+        return NT == 64 ? launch_conv<64, true, true>(m, p, s) : launch_conv<128, true, true>(m, p, s);
     if (passes == 2) return NT == 64 ? launch_conv<64, true>(m, p, s) : launch_conv<128, true>(m, p, s);
 #endif
     if (halo && two_env)

@@ -38,7 +38,7 @@ def split(ops, x, prescale=1.0):
 def test_library_loaded_and_device_ok():
     from diffsep_b200 import _lib
     lib = _lib.load()
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 6
     assert lib.dsep_device_ok() == 1
 
 
