@@ -98,7 +98,8 @@ class ConvWeight:
 
 
     # ---- passes = 2: e4m3 correction plane
-    A8_EXP = 3            # activations enter the e4m3 planes as A_hi * 2^3 (saturating above 56) and A_lo * 2^14
+    A8_EXP = 0            # activations enter the e4m3 planes as A_hi (saturating above 448) and A_lo * 2^11; with no
+                          # prescale the builder converts A_hi8 straight from the packed fp16 pairs
     W8_EXP = -3           # fp16 weight planes hold |W * 2^k| < 2048: W_hi * 2^-3 < 256 and W_lo * 2^8 <= 128 fit e4m3
 
     def planes8(self) -> Split:

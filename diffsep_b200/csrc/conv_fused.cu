@@ -1,0 +1,583 @@
+// The network's dominant launch: 3x3 / 1x1 convolution on tcgen05 with the GroupNorm-apply + SiLU + channel
+// concat + operand split of its input done in-kernel, role-split so that no role waits on another's latency.
+//
+//   out = scale * ( acc_scale * ( conv(act(x * sc + sh)) + conv1x1(shortcut) ) + bias + film + residual )
+//
+// Same arithmetic, operand layouts and barriers-by-name as conv_tc_kernel<NT, halo> (conv_tc.cu), which this
+// kernel replaces for Cout >= 64 whenever the main operand is built in-kernel.  What changed, and why
+// (profiles/conv_modes_r2a.md): in the 2-unit mode (fp16 hi*hi + one e4m3 product for both corrections) the
+// tensor core needs 0.74 ms for the level-0 conv but the 8 worker warps that both BUILT the operand patches and
+// RAN the epilogue needed 1.11 ms on their own — issue slots 38 % used, the rest exposed latency: each patch's
+// global loads were issued and immediately waited for, and the epilogue's TMEM / shared / global round trips
+// sat in the same instruction stream.  Here:
+//   * 16 warps.  Warpgroup 0: TMA weight producer (warp 0), MMA issuer (warp 1, convergent, descriptors in
+//     uniform registers), TMEM allocator (warp 2).  Warpgroups 1-2: eight BUILDER warps.  Warpgroup 3: four
+//     EPILOGUE warps (one per TMEM lane quarter).  setmaxnreg: 56 / 152 / 152 (128 x 56 + 384 x 152 = 65536).
+//   * builders prefetch: while patch n is converted and stored, the global loads of patch n + 1 are already in
+//     flight into the registers patch n just vacated (one 16-byte pair of loads re-issued per converted pair), so
+//     a patch's load latency overlaps a whole patch of arithmetic — across tile and K-block boundaries.  One
+//     code path serves both patch geometries (10 x 18 halo patch of a 3x3 conv, 8 x 16 of a 1x1 / shortcut).
+//   * the epilogue never blocks a builder: it runs a full tile behind the MMAs (double-buffered TMEM).
+#include "conv_tc.cuh"
+
+namespace dsep {
+
+constexpr int kFThreads = 512;
+constexpr int kFBuilderWarps = 8;
+constexpr int kFEpiWarps = 4;
+constexpr int kFNA = 2;                    // A-patch ring slots
+
+template <int NT>
+struct FusedCfg {
+    static constexpr int kBBytes = NT * 128;                   // one weight plane of a stage (64 channels)
+    static constexpr int kAStage = 2 * kPatchPlane;
+    static constexpr int kBStage = 2 * kBBytes;
+    static constexpr int kStagingBytes = kFEpiWarps * 32 * 32 * 4;
+    static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes - kFNA * kAStage;
+    static constexpr int kBStagesMax = kAvail / kBStage;
+    static constexpr int kBStages = kBStagesMax > 8 ? 8 : kBStagesMax;
+    static constexpr int kRingBytes = kFNA * kAStage + kBStages * kBStage;
+    static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 512 + 1024;
+    static constexpr int kTmemCols = 4 * NT;                   // 2 accumulator stages x (main | correction) x NT
+};
+
+// One builder thread's view of one patch: its rows are r = r0 + u * krows (u < niter), all in one patch column,
+// kdy image rows apart — 10 x 18 halo patch: krows 30, niter 6 (threads with r0 >= 30 idle); 8 x 16: 32, 4.
+struct PatchPlan {
+    const float* src;      // this thread's 8 channels of row u = 0 (only dereferenced where inb says so)
+    uint32_t step;         // elements between rows u and u + 1
+    uint32_t inb;          // bit u: row u exists and lies inside the image
+    uint32_t krows;        // 30 / 32
+    uint32_t niter;        // 6 / 4 (0: this thread has no rows)
+    uint32_t so;           // index of this thread's 8 channels in the sc / sh tables
+    int mode;              // 0 raw (shortcut operand), 1 affine, 2 affine + SiLU
+    bool second;           // shortcut K-block (fp16 (hi, lo) planes even in the e4m3 mode)
+};
+
+__device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+    return r;
+}
+
+// Converts one pair of float4 (8 consecutive channels of one patch row) and stores the row chunk of both planes.
+//   MODE 0: y = x;  1: y = x * sc + sh;  2: SiLU of that.   E4M3: second plane = [A_lo8 x 8 | A_hi8 x 8].
+template <int MODE, bool E4M3>
+__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, const float (&k_sc)[8],
+                                              const float (&k_sh)[8], bool inside, uint32_t dst_hi, uint32_t dst_2,
+                                              float a8_hi, float a8_lo) {
+    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+    if (inside) {
+        float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        if (MODE != 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = fmaf(y[e], k_sc[e], k_sh[e]);
+                if (MODE == 2) {   // SiLU = t / (1 + 2^(-t log2 e)): ex2.approx.ftz + rcp.approx.ftz, no range fix-ups
+                    float ex, rc;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t * -1.4426950408889634f));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+                    t *= rc;
+                }
+                y[e] = t;
+            }
+        }
+        if (E4M3) {
+            float l[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(y[2 * e + 1]), "f"(y[2 * e]));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+                l[2 * e] = (y[2 * e] - b.x) * a8_lo;
+                l[2 * e + 1] = (y[2 * e + 1] - b.y) * a8_lo;
+            }
+            lo[0] = e4m3x4(l[0], l[1], l[2], l[3]);
+            lo[1] = e4m3x4(l[4], l[5], l[6], l[7]);
+            if (a8_hi == 1.0f) {       // A_hi8 straight from the packed fp16 pairs
+                lo[2] = e4m3x2_from_f16x2(hi[0]) | (e4m3x2_from_f16x2(hi[1]) << 16);
+                lo[3] = e4m3x2_from_f16x2(hi[2]) | (e4m3x2_from_f16x2(hi[3]) << 16);
+            } else {
+                float h[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+                    h[2 * e] = b.x * a8_hi; h[2 * e + 1] = b.y * a8_hi;
+                }
+                lo[2] = e4m3x4(h[0], h[1], h[2], h[3]);
+                lo[3] = e4m3x4(h[4], h[5], h[6], h[7]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
+        }
+    }
+    sts128(dst_hi, hi[0], hi[1], hi[2], hi[3]);
+    sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
+}
+
+// Converts the thread's rows of the CURRENT patch out of v[][] into the ring slot at `slot_addr` while the rows of
+// the NEXT patch are loaded into the registers just vacated.
+template <int MODE, bool E4M3>
+__device__ __forceinline__ void build_rows(float4 (&v)[6][2], const PatchPlan& cur, const PatchPlan& nxt, bool have_next,
+                                           const float* __restrict__ sc, const float* __restrict__ sh, uint32_t slot_addr,
+                                           uint32_t r0, uint32_t jchunk, float a8_hi, float a8_lo) {
+    float k_sc[8], k_sh[8];
+    if (MODE != 0) {
+        if (sc != nullptr) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + cur.so));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(sc + cur.so + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(sh + cur.so));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(sh + cur.so + 4));
+            k_sc[0] = a0.x; k_sc[1] = a0.y; k_sc[2] = a0.z; k_sc[3] = a0.w;
+            k_sc[4] = a1.x; k_sc[5] = a1.y; k_sc[6] = a1.z; k_sc[7] = a1.w;
+            k_sh[0] = b0.x; k_sh[1] = b0.y; k_sh[2] = b0.z; k_sh[3] = b0.w;
+            k_sh[4] = b1.x; k_sh[5] = b1.y; k_sh[6] = b1.z; k_sh[7] = b1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { k_sc[e] = 1.0f; k_sh[e] = 0.0f; }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+        if (u < static_cast<int>(cur.niter)) {
+            const uint32_t r = r0 + static_cast<uint32_t>(u) * cur.krows;
+            const uint32_t off = r * 128u + ((jchunk ^ (r & 7u)) << 4);
+            convert_store<MODE, E4M3>(v[u][0], v[u][1], k_sc, k_sh, ((cur.inb >> u) & 1u) != 0, slot_addr + off,
+                                      slot_addr + kPatchPlane + off, a8_hi, a8_lo);
+        }
+        if (have_next && ((nxt.inb >> u) & 1u)) {
+            const float* q = nxt.src + static_cast<size_t>(u) * nxt.step;
+            v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
+            v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
+        }
+    }
+}
+
+template <int NT, bool FP8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                  const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+                  const ConvParams p) {
+    using Cfg = FusedCfg<NT>;
+    constexpr int NS = Cfg::kBStages;
+    constexpr int NA = kFNA;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    float* staging = reinterpret_cast<float*>(smem + Cfg::kRingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes + Cfg::kStagingBytes);
+    uint64_t* full = bars;             // [NS]   weights: TMA -> MMA
+    uint64_t* empty = bars + NS;       // [NS]   MMA -> TMA (both CTAs of the pair commit)
+    uint64_t* tfull = bars + 2 * NS;   // [2]    MMA -> epilogue
+    uint64_t* tempty = tfull + 2;      // [2]    epilogue -> MMA
+    uint64_t* afull = tempty + 2;      // [NA]   patches: builders -> MMA
+    uint64_t* aempty = afull + NA;     // [NA]   MMA -> builders
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty + NA);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_w_hi);
+        tma_prefetch_desc(&tm_w_lo);
+        if (p.kblocks2 > 0) { tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kFEpiWarps); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], kFBuilderWarps); mbar_init(&aempty[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // both CTAs' barriers are initialised before any multicast targets them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int total_patches = p.kblocks + p.kblocks2;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && lane == 0) {
+            // ------------------------------------------------------------------ TMA producer: weight stages
+            int bs = 0;
+            uint32_t bph = 0;
+            auto load_weights = [&](const CUtensorMap* whi, const CUtensorMap* wlo, int kcol, int wrow) {
+                mbar_wait(&empty[bs], bph ^ 1u);
+                uint8_t* sb = stage_base + NA * Cfg::kAStage + bs * Cfg::kBStage;
+                if (p.debug & 2) {
+                    mbar_arrive(&full[bs]);
+                } else {
+                    // each CTA of the pair fetches half of the rows of both planes and multicasts them to both
+                    mbar_arrive_expect_tx(&full[bs], 2u * Cfg::kBBytes);
+                    const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);
+                    const int boff = static_cast<int>(rank) * (Cfg::kBBytes / 2);
+                    tma_load_2d_mc(sb + boff, whi, &full[bs], kcol, wrow_h, 0x3);
+                    tma_load_2d_mc(sb + Cfg::kBBytes + boff, wlo, &full[bs], kcol, wrow_h, 0x3);
+                }
+                if (++bs == NS) { bs = 0; bph ^= 1u; }
+            };
+            for (int item = cluster_id; item < p.total_items; item += num_clusters) {
+                const int n0 = (item % p.tiles_n) * NT;
+                for (int kb = 0; kb < p.kblocks2; ++kb) load_weights(&tm_w2_hi, &tm_w2_lo, kb * 64, n0);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    for (int tap = 0; tap < p.taps; ++tap)
+                        load_weights(&tm_w_hi, &tm_w_lo, kb * 64, tap * p.Cout_pad + n0);
+            }
+        } else if (warp == 1) {
+            // ------------------------------------------------------------------ MMA issuer
+            // the WHOLE warp walks the pipeline convergently and one elected lane issues: barrier addresses,
+            // descriptors and the accumulate flag stay in uniform registers (see conv_tc.cu)
+            const bool leader = elect_one();
+            constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
+            constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
+            constexpr uint32_t kHiPatch = ((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t kHiPlain = (1024u >> 4) | (1u << 14) | (2u << 29);
+            auto desc = [](uint32_t lo, uint32_t hi) {
+                uint64_t d;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+                return d;
+            };
+            const uint32_t a_ring = smem_u32(stage_base) >> 4;
+            const uint32_t b_ring = smem_u32(stage_base + NA * Cfg::kAStage) >> 4;
+            const bool do_mma = !(p.debug & 1);
+            int bs = 0, as_ = 0;
+            uint32_t bph = 0, aph = 0;
+            int it = 0;
+            for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 2 * NT;
+                uint32_t accumulate = 0, accumulate8 = 0;
+                auto issue = [&](uint32_t a_word, uint32_t a_hiword, bool main_kb) {
+                    mbar_wait(&full[bs], bph);
+                    tc_fence_after();
+                    const uint32_t b_word = b_ring + bs * (Cfg::kBStage >> 4);
+                    if (leader) {
+                        if (do_mma) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a_hi = desc(a_word + 2 * k, a_hiword);
+                                const uint64_t a_2 = desc(a_word + (kPatchPlane >> 4) + 2 * k, a_hiword);
+                                const uint64_t b_hi = desc(b_word + 2 * k, kHiPlain);
+                                const uint64_t b_2 = desc(b_word + (Cfg::kBBytes >> 4) + 2 * k, kHiPlain);
+                                if (FP8) {
+                                    umma_f16(d_tmem, a_hi, b_hi, idesc_n, accumulate);             // hi*hi -> [0, NT)
+                                    if (main_kb) {   // [A_lo8 | A_hi8] x [W_hi8 ; W_lo8], K = 32 -> [NT, 2NT)
+                                        umma_e4m3(d_tmem + NT, a_2, b_2, idesc_n, accumulate8);
+                                        accumulate8 = 1;
+                                    } else {         // fp16 shortcut K-block: the two corrections join [0, NT)
+                                        umma_f16(d_tmem, a_hi, b_2, idesc_n, 1);
+                                        umma_f16(d_tmem, a_2, b_hi, idesc_n, 1);
+                                    }
+                                } else {             // A_hi x [W_hi ; W_lo] (N = 2NT) and A_lo x W_hi
+                                    umma_f16(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
+                                    umma_f16(d_tmem, a_2, b_hi, idesc_n, 1);
+                                }
+                                accumulate = 1;
+                            }
+                        }
+                        umma_commit_mc(&empty[bs], 0x3);      // frees the weight slot in BOTH CTAs
+                    }
+                    __syncwarp();
+                    if (++bs == NS) { bs = 0; bph ^= 1u; }
+                };
+                for (int pi = 0; pi < total_patches; ++pi) {
+                    const bool second = pi < p.kblocks2;
+                    mbar_wait(&afull[as_], aph);
+                    tc_fence_after();
+                    const uint32_t sa = a_ring + as_ * (Cfg::kAStage >> 4);
+                    if (!second && p.taps == 9) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap)
+                            issue(sa + ((tap / 3) * kPatchW + tap % 3) * 8, kHiPatch, true);
+                    } else {
+                        issue(sa, kHiPlain, !second);
+                    }
+                    if (leader) umma_commit(&aempty[as_]);
+                    __syncwarp();
+                    if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                }
+                if (leader) umma_commit(&tfull[acc]);
+                __syncwarp();
+            }
+        }
+    } else if (warp < 4 + kFBuilderWarps) {
+        // ---------------------------------------------------------------------- patch builders
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        const int wtid = static_cast<int>(threadIdx.x) - 128;
+        const uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
+        const uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
+        const uint32_t a_ring = smem_u32(stage_base);
+        const bool skip = (p.debug & 2) != 0;
+        const float a8_hi = FP8 ? p.a8_hi : 0.f, a8_lo = FP8 ? p.a8_lo : 0.f;
+
+        // generator of this CTA's patch sequence: tiles in schedule order, per tile the shortcut K-blocks then the
+        // main ones (the order the MMA issuer consumes them in)
+        int g_item = cluster_id, g_pi = 0;
+        int g_w0 = 0, g_h0 = 0, g_b0 = 0;
+        auto locate = [&]() {
+            int r = 2 * (g_item / p.tiles_n) + static_cast<int>(rank);
+            const int wt = r % p.tiles_w; r /= p.tiles_w;
+            const int ht = r % p.tiles_h; r /= p.tiles_h;
+            g_w0 = wt << 3; g_h0 = ht << 4; g_b0 = r;
+        };
+        bool g_valid = g_item < p.total_items;
+        if (g_valid) locate();
+        auto next_plan = [&](PatchPlan& d) {            // plan of (g_item, g_pi), then advance
+            const bool second = g_pi < p.kblocks2;
+            const bool halo3 = !second && p.taps == 9;
+            const int kb = second ? g_pi : g_pi - p.kblocks2;
+            const int c = kb * 64 + static_cast<int>(jchunk) * 8;
+            const float* x0 = second ? p.gx0 : p.fx0;
+            const float* x1 = second ? p.gx1 : p.fx1;
+            const int C0 = second ? p.gC0 : p.fC0, C1 = second ? p.gC1 : p.fC1;
+            const float* src; int cs, cl;
+            if (c < C0) { src = x0; cs = C0; cl = c; } else { src = x1; cs = C1; cl = c - C0; }
+            const int PW = halo3 ? kPatchW : 8, kdy = halo3 ? 3 : 4;
+            d.krows = halo3 ? 30u : 32u;
+            d.niter = r0 < d.krows ? (halo3 ? 6u : 4u) : 0u;
+            const int py0 = static_cast<int>(r0) / PW, px0 = static_cast<int>(r0) - py0 * PW;
+            const int w = g_w0 - (halo3 ? 1 : 0) + px0;
+            const int h0 = g_h0 - (halo3 ? 1 : 0) + py0;
+            const bool col_ok = d.niter != 0u && g_b0 < p.B && w >= 0 && w < p.W;
+            d.src = src + (((static_cast<long long>(g_b0) * p.H + h0) * p.W + w) * cs + cl);
+            d.step = static_cast<uint32_t>(kdy * p.W * cs);
+            uint32_t inb = 0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int h = h0 + kdy * u;
+                if (col_ok && u < static_cast<int>(d.niter) && h >= 0 && h < p.H) inb |= 1u << u;
+            }
+            d.inb = skip ? 0u : inb;
+            d.so = static_cast<uint32_t>((g_b0 < p.B ? g_b0 : 0) * (C0 + C1) + c);
+            d.second = second;
+            d.mode = second ? 0 : (p.fsc != nullptr ? (p.fact ? 2 : 1) : 1);
+            if (++g_pi == total_patches) {
+                g_pi = 0;
+                g_item += num_clusters;
+                g_valid = g_item < p.total_items;
+                if (g_valid) locate();
+            }
+        };
+
+        float4 v[6][2];
+        PatchPlan cur, nxt;
+        if (g_valid) {
+            next_plan(cur);
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                if ((cur.inb >> u) & 1u) {
+                    const float* q = cur.src + static_cast<size_t>(u) * cur.step;
+                    v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
+                    v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
+                }
+            }
+            int as_ = 0;
+            uint32_t aph = 0;
+            while (true) {
+                const bool have_next = g_valid;
+                if (have_next) next_plan(nxt);
+                const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
+                mbar_wait(&aempty[as_], aph ^ 1u);
+                if (cur.second)
+                    build_rows<0, false>(v, cur, nxt, have_next, nullptr, nullptr, slot, r0, jchunk, 0.f, 0.f);
+                else if (cur.mode == 2)
+                    build_rows<2, FP8>(v, cur, nxt, have_next, p.fsc, p.fsh, slot, r0, jchunk, a8_hi, a8_lo);
+                else
+                    build_rows<1, FP8>(v, cur, nxt, have_next, p.fsc, p.fsh, slot, r0, jchunk, a8_hi, a8_lo);
+                // each builder warp publishes its own share (afull counts the builder warps)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull[as_]);
+                if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+                if (!have_next) break;
+                cur = nxt;
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- epilogue (4 warps)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        const int wq = warp & 3;               // TMEM lane quarter == warp_id % 4
+        const float crel = FP8 ? p.corr_rel : 1.0f;
+        constexpr int kChunks = NT / 32;       // 32-column chunks of the tile, all handled by this warp
+        float4 run1[kChunks], run2[kChunks];   // GroupNorm partial sums of this thread's 4 channels per chunk
+        int run_b = -1, run_n0 = -1;
+        auto flush_stats = [&]() {
+            if (p.stats == nullptr || run_b < 0) return;           // warp-uniform
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {                     // rows of the 4 lane groups -> lanes 0..7
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                    run1[c].x += __shfl_xor_sync(0xffffffffu, run1[c].x, o);
+                    run1[c].y += __shfl_xor_sync(0xffffffffu, run1[c].y, o);
+                    run1[c].z += __shfl_xor_sync(0xffffffffu, run1[c].z, o);
+                    run1[c].w += __shfl_xor_sync(0xffffffffu, run1[c].w, o);
+                    run2[c].x += __shfl_xor_sync(0xffffffffu, run2[c].x, o);
+                    run2[c].y += __shfl_xor_sync(0xffffffffu, run2[c].y, o);
+                    run2[c].z += __shfl_xor_sync(0xffffffffu, run2[c].z, o);
+                    run2[c].w += __shfl_xor_sync(0xffffffffu, run2[c].w, o);
+                }
+            }
+            if (run_b >= p.B || (lane >> 3) != 0) return;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int n = run_n0 + c * 32 + (lane & 7) * 4;
+                if (n < p.cout_store) {
+                    double* st = p.stats + (static_cast<size_t>(run_b) * p.cout_store + n) * 2;
+                    atomicAdd(st + 0, (double)run1[c].x); atomicAdd(st + 1, (double)run2[c].x);
+                    atomicAdd(st + 2, (double)run1[c].y); atomicAdd(st + 3, (double)run2[c].y);
+                    atomicAdd(st + 4, (double)run1[c].z); atomicAdd(st + 5, (double)run2[c].z);
+                    atomicAdd(st + 6, (double)run1[c].w); atomicAdd(st + 7, (double)run2[c].w);
+                }
+            }
+        };
+        const uint32_t stg_s = smem_u32(staging + wq * (32 * 32));
+        const int q = lane & 7, rg = lane >> 3;
+        const uint32_t st_base = stg_s + lane * 128 + ((lane & 7) << 4);     // chunk j at ^ (j << 4)
+        const uint32_t ld_base = stg_s + rg * 128 + ((q ^ rg) << 4);         // row i at + i*512, ^ ((i&1) << 6)
+        const float as2 = p.acc_scale * p.scale;
+        const bool store = !(p.debug & 4);
+        int it = 0;
+        for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
+            const int as = it & 1;
+            const int nt = item % p.tiles_n;
+            int r = 2 * (item / p.tiles_n) + static_cast<int>(rank);      // this CTA's M tile of the pair
+            const int wt = r % p.tiles_w; r /= p.tiles_w;
+            const int ht = r % p.tiles_h; r /= p.tiles_h;
+            // r >= B only for the odd tile out of the last pair: its patches were zero and every store is masked
+            const int w0 = wt << 3, h0 = ht << 4, b0 = r;
+            const int n0 = nt * NT;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 2 * NT;
+            if (p.stats != nullptr && (b0 != run_b || n0 != run_n0)) {
+                flush_stats();
+                run_b = b0; run_n0 = n0;
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) run1[c] = run2[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const bool whole = b0 < p.B && h0 + 16 <= p.H && w0 + 8 <= p.W && n0 + NT <= p.cout_store;
+            // row i of this thread: pixel (h0 + wq*4 + (i >> 1), w0 + rg + 4*(i & 1)), 4 channels from n
+            const int hrow = h0 + wq * 4, wcol = w0 + rg;
+            const uint32_t C = static_cast<uint32_t>(p.cout_store);
+            const size_t e0 = ((static_cast<size_t>(b0 < p.B ? b0 : 0) * p.H + hrow) * p.W + wcol) * C + n0 + q * 4;
+            float* const out0 = p.out + e0;
+            const float* const res0 = p.residual != nullptr ? p.residual + e0 : nullptr;
+            const uint32_t d_row = static_cast<uint32_t>(p.W) * C;      // i -> i + 2: next image row
+            const uint32_t d_half = 4u * C;                            // odd i: 4 pixels to the right
+            // rows of this thread that exist (partial tiles at the map's edge; all 8 when `whole`)
+            uint32_t rowmask = 0xFFu;
+            if (!whole) {
+                rowmask = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (b0 < p.B && hrow + (i >> 1) < p.H && wcol + 4 * (i & 1) < p.W) rowmask |= 1u << i;
+            }
+            bool waited = false;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                const int n = n0 + c * 32 + q * 4;
+                const bool n_ok = whole || n < p.cout_store;
+                float4 res[8];
+                if (res0 != nullptr) {     // prefetch the residual while the accumulator is still being produced
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        res[i] = (n_ok && ((rowmask >> i) & 1u))
+                                     ? __ldg(reinterpret_cast<const float4*>(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n_ok) {
+                    if (p.bias != nullptr) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    if (p.film != nullptr && b0 < p.B) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(
+                            p.film + static_cast<size_t>(b0) * p.film_stride + n));
+                        bz.x += f.x; bz.y += f.y; bz.z += f.z; bz.w += f.w;
+                    }
+                }
+                bz.x *= p.scale; bz.y *= p.scale; bz.z *= p.scale; bz.w *= p.scale;
+                if (!waited) {
+                    mbar_wait(&tfull[as], (it >> 1) & 1);
+                    tc_fence_after();
+                    waited = true;
+                }
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + c * 32, v);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {   // add the correction / hi*lo half, 16 columns at a time
+                    uint32_t u[16];
+                    tmem_ld_32x16(t_addr + NT + c * 32 + hh * 16, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[hh * 16 + j] = __float_as_uint(fmaf(__uint_as_float(u[j]), crel, __uint_as_float(v[hh * 16 + j])));
+                }
+                if (c == kChunks - 1) {   // TMEM fully drained by this warp: hand the buffer back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sts128(st_base ^ (j << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 a = lds128((ld_base ^ ((i & 1) << 6)) + i * 512);
+                    if (n_ok && ((rowmask >> i) & 1u)) {
+                        a.x = fmaf(a.x, as2, bz.x); a.y = fmaf(a.y, as2, bz.y);
+                        a.z = fmaf(a.z, as2, bz.z); a.w = fmaf(a.w, as2, bz.w);
+                        if (res0 != nullptr) {
+                            a.x = fmaf(res[i].x, p.scale, a.x); a.y = fmaf(res[i].y, p.scale, a.y);
+                            a.z = fmaf(res[i].z, p.scale, a.z); a.w = fmaf(res[i].w, p.scale, a.w);
+                        }
+                        if (store)
+                            *reinterpret_cast<float4*>(out0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half) = a;
+                        s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+                        s2.x = fmaf(a.x, a.x, s2.x); s2.y = fmaf(a.y, a.y, s2.y);
+                        s2.z = fmaf(a.z, a.z, s2.z); s2.w = fmaf(a.w, a.w, s2.w);
+                    }
+                }
+                if (p.stats != nullptr) {
+                    run1[c].x += s1.x; run1[c].y += s1.y; run1[c].z += s1.z; run1[c].w += s1.w;
+                    run2[c].x += s2.x; run2[c].y += s2.y; run2[c].z += s2.z; run2[c].w += s2.w;
+                }
+                __syncwarp();
+            }
+        }
+        flush_stats();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer may still multicast into / arrive on this CTA's shared memory
+    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int NT, bool FP8>
+static int launch_fused(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
+    constexpr int kSmem = FusedCfg<NT>::kSmemBytes;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_fused_kernel<NT, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    });
+    if (attr_err != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_fused_kernel<%d,%d>): %s", NT, (int)FP8, cudaGetErrorString(attr_err));
+        return DSEP_ERR_CUDA;
+    }
+    const int max_clusters = conv_num_sms() / 2;
+    const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
+    conv_fused_kernel<NT, FP8><<<grid, kFThreads, kSmem, stream>>>(m.w_hi, m.w_lo, m.w2_hi, m.w2_lo, p);
+    return check_launch("conv_fused_kernel");
+}
+
+int launch_conv_fused(const ConvMaps& m, const ConvParams& p, int NT, cudaStream_t stream) {
+    if (p.passes == 2) return NT == 64 ? launch_fused<64, true>(m, p, stream) : launch_fused<128, true>(m, p, stream);
+    return NT == 64 ? launch_fused<64, false>(m, p, stream) : launch_fused<128, false>(m, p, stream);
+}
+
+}  // namespace dsep

@@ -35,63 +35,9 @@
 //     transpose (conflict-free both ways) -> bias/FiLM/residual/scale fused -> 128-byte
 //     coalesced fp32 stores; per-channel (sum, sum^2) reduced in registers + 2 shuffles and
 //     accumulated with fp64 atomics.
-#include <stdlib.h>
-
-#include <mutex>
-
-#include "common.cuh"
-
-// passes = 2 (the product default; -DDSEP_FP8_CORR=0 compiles it out): per K=16 step ONE fp16 product hi*hi plus
-// ONE e4m3 tensor-core product that carries both correction terms, [A_lo8 | A_hi8] x [W_hi8 ; W_lo8] (K = 32
-// bytes, twice the fp16 rate) = 2 tensor-core units per MAC instead of 3.  tools/numerics_study.py: network error
-// 4.7e-5 from the operand rounding (budget 1e-4; dropping either correction in a single level-0 conv costs
-// 2.4e-4).  Halo kernel only (maps of at least 16 x 8, Cout >= 64); the main operand is either built in-kernel
-// or arrives as (fp16 hi, e4m3 correction) planes by TMA (dsep_fir_resample8 writes them).
-#ifndef DSEP_FP8_CORR
-#define DSEP_FP8_CORR 1
-#endif
+#include "conv_tc.cuh"
 
 namespace dsep {
-
-struct ConvParams {
-    int B, H, W, Cin, Cout_pad, cout_store;
-    int taps;              // 1 or 9
-    int tw_log2, th_log2;  // pixel tile: tw x th x tb = 128
-    int tiles_w, tiles_h, tiles_b, tiles_n, total_items;   // item = (pair of M-adjacent tiles, channel tile)
-    int kblocks;           // Cin / kBK
-    int kblocks2;          // Cin2 / kBK of the fused 1x1 shortcut (0: none)
-    int passes;            // 1 or 3
-    const float* bias;
-    const float* film;
-    int film_stride;
-    const float* residual;
-    float scale, acc_scale;
-    float* out;
-    double* stats;         // [B, cout_store, 2] or null
-    // fused prologue (halo mode): the A patch is built in-kernel from fp32 activations instead of
-    // arriving as split planes by TMA.  main operand: act(x * sc + sh) of the channel-concatenated
-    // [fx0 (fC0 ch) | fx1 (fC1 ch)]; shortcut operand: the raw [gx0 | gx1] (identity).
-    const float* fx0; const float* fx1; int fC0, fC1;
-    const float* fsc; const float* fsh; int fact;
-    const float* gx0; const float* gx1; int gC0, gC1;
-#if DSEP_FP8_CORR
-    float corr_rel;        // passes = 2: weight of the e4m3 correction accumulator relative to the fp16 one
-    float a8_hi, a8_lo;    // passes = 2: power-of-two prescales of the e4m3 activation planes (A_hi, A_lo)
-#endif
-    int debug;             // DSEP_CONV_DEBUG bitmask: 1 skip MMA issue, 2 skip TMA loads, 4 skip epilogue stores (timing experiments)
-};
-
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 128 + kEpiWarps * 32;
-// K-block: channels per pipeline stage.  64 (128-byte swizzle) is the default; 32 (64-byte swizzle,
-// twice as many half-size stages) was measured 16 % slower: the operand feed is bound by L2->SM
-// delivery (~12.6 TB/s with 128-byte rows, ~7 TB/s with 64-byte rows), not by ring depth.
-#ifndef DSEP_CONV_BK
-#define DSEP_CONV_BK 64
-#endif
-constexpr int kBK = DSEP_CONV_BK;
-static_assert(kBK == 32 || kBK == 64, "K-block must be 32 or 64 channels");
-constexpr int kABytes = 128 * kBK * 2;     // one A plane of a stage
 
 template <int NT>
 struct ConvCfg {
@@ -106,19 +52,6 @@ struct ConvCfg {
 };
 
 
-// ---- "halo" mode (3x3, maps of at least 16 x 8): the A operand of all nine taps comes from ONE
-// shared-memory patch.  The output tile is 8 (w) x 16 (h) pixels; its 10 x 18 input patch of 64
-// channels is a single TMA box (out-of-image pixels zero-filled).  Patch row = y_p * 10 + x_p, so the
-// 128 operand rows of tap (dy, dx) are 16 groups of 8 consecutive patch rows starting at row
-// dy * 10 + dx, 10 rows (1280 B) apart: exactly a K-major UMMA descriptor with SBO = 1280 and a
-// shifted start address (the 128-byte swizzle is a function of the shared-memory address, which TMA
-// and tcgen05.mma share).  Shared-memory ingest per tile drops from 1152 KB to 668 KB, which is what
-// bounded the per-tap kernel (TMA-only time 1.0 ms vs MMA-only 1.2 ms on the level-0 conv).
-constexpr int kPatchW = 10, kPatchH = 18;
-constexpr int kPatchBytes = kPatchW * kPatchH * 128;          // 23040: one plane of a patch
-constexpr int kPatchPlane = 23 * 1024;                         // its 1024-aligned slot
-constexpr int kHaloAStages = 2;
-
 template <int NT>
 struct HaloCfg {
     static constexpr int kBBytes = NT * 128;                   // one weight plane of a stage (64 ch)
@@ -131,28 +64,6 @@ struct HaloCfg {
     static constexpr int kSmemBytes = kHaloAStages * kAStage + kBStages * kBStage + kStagingBytes + 512 + 1024;
 };
 
-
-// Builds one 64-channel A patch (PH x PW pixels, row = py * PW + px, 128-byte-swizzled K-major rows of
-// (hi, lo) fp16) from fp32 activations: y = act(x * sc[c] + sh[c]), zero outside the image (the conv
-// pads the ACTIVATED tensor).  Called by the kBuilders builder threads; wtid = 0..255.  Replaces the
-// GroupNorm-apply + SiLU + split pass (and the channel concat) that used to run as its own kernel.
-constexpr int kBuilders = 256;   // the 8 worker warps (two warpgroups, 224 registers each after setmaxnreg)
-
-// (hi, lo) fp16 pairs of two floats; out-of-range values saturate to +-65504 instead of becoming NaN
-__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - back.y), "f"(a - back.x));
-}
-
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 
 // One builder thread's share of a patch.  Item = (patch row r, 8-channel chunk j); thread wtid owns chunk
 // j = wtid & 7 of rows r0 + kRows u (r0 = wtid >> 3).  kRows is a multiple of the patch width (32 for 8-wide
@@ -222,16 +133,6 @@ __device__ __forceinline__ void patch_load(PatchRegs<PW, PH>& R, const float* x0
 
 // phase 2: y = act(x * sc + sh) (zero outside the image: the conv pads the ACTIVATED tensor), fp32 -> (hi, lo)
 // fp16 split, 128-byte-swizzled K-major rows.  dst_hi / dst_lo are shared-window addresses of the two planes.
-#if DSEP_FP8_CORR
-// 8 activations -> 16 bytes of the e4m3 correction plane: [A_lo8 x 8 | A_hi8 x 8] (the weight plane holds
-// [W_hi8 x 8 | W_lo8 x 8] at the same bytes, so the K = 32 product sums A_lo*W_hi + A_hi*W_lo)
-__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
-    uint16_t p0, p1;
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p0) : "f"(b), "f"(a));
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(p1) : "f"(d), "f"(c));
-    return static_cast<uint32_t>(p0) | (static_cast<uint32_t>(p1) << 16);
-}
-#endif
 
 template <int PW, int PH>
 __device__ __forceinline__ void patch_store(const PatchRegs<PW, PH>& R, uint32_t dst_hi, uint32_t dst_lo, bool want_lo,
@@ -1144,7 +1045,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     return DSEP_OK;
 }
 
-static int num_sms() {
+int conv_num_sms() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
@@ -1154,10 +1055,6 @@ static int num_sms() {
     }
     return n;
 }
-
-struct ConvMaps {
-    CUtensorMap a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, w2_hi, w2_lo;
-};
 
 template <int NT, bool HALO, bool TWO = false>
 static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
@@ -1171,7 +1068,7 @@ static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stre
         set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>): %s", NT, (int)HALO, cudaGetErrorString(attr_err));
         return DSEP_ERR_CUDA;
     }
-    const int max_clusters = num_sms() / 2;
+    const int max_clusters = conv_num_sms() / 2;
     const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
     conv_tc_kernel<NT, HALO, TWO><<<grid, kThreads, kSmem, stream>>>(
         m.a_hi, m.a_lo, m.w_hi, m.w_lo, m.a2_hi, m.a2_lo, m.w2_hi, m.w2_lo, p);
@@ -1327,6 +1224,10 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
+    // Cout >= 64 with the operand built in-kernel: the role-split kernel of conv_fused.cu (DSEP_CONV_V2=0: the
+    // previous one-worker-role halo kernel below, kept for A/B timing)
+    static const int v2_env = getenv("DSEP_CONV_V2") ? atoi(getenv("DSEP_CONV_V2")) : 1;
+    if (halo && main_fused && NT >= 64 && passes != 1 && v2_env != 0 && !two_env) return launch_conv_fused(m, p, NT, s);
     if (halo && NT == 16) return launch_conv<16, true>(m, p, s);
 #if DSEP_FP8_CORR
     if (passes == 2 && two_env)
