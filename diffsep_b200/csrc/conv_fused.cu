@@ -12,11 +12,12 @@
 // sat in the same instruction stream.  Here:
 //   * 16 warps.  Warpgroup 0: TMA weight producer (warp 0), MMA issuer (warp 1, convergent, descriptors in
 //     uniform registers), TMEM allocator (warp 2).  Warpgroups 1-2: eight BUILDER warps.  Warpgroup 3: four
-//     EPILOGUE warps (one per TMEM lane quarter).  setmaxnreg: 56 / 152 / 152 (128 x 56 + 384 x 152 = 65536).
-//   * builders prefetch: while patch n is converted and stored, the global loads of patch n + 1 are already in
-//     flight into the registers patch n just vacated (one 16-byte pair of loads re-issued per converted pair), so
-//     a patch's load latency overlaps a whole patch of arithmetic — across tile and K-block boundaries.  One
-//     code path serves both patch geometries (10 x 18 halo patch of a 3x3 conv, 8 x 16 of a 1x1 / shortcut).
+//     EPILOGUE warps (one per TMEM lane quarter).  setmaxnreg: 40 / 152 / 152 (128 x 40 + 384 x 152
+//     = 63488 of 65536 registers).
+//   * builders prefetch: while patch n is converted and stored out of one register set, the global loads of patch
+//     n + 1 are in flight into a second set (issued in one burst at the start of patch n), so a patch's load latency
+//     overlaps a whole patch of arithmetic — across tile and K-block boundaries.  One code path serves both patch
+//     geometries (10 x 18 halo patch of a 3x3 conv, 8 x 16 of a 1x1 / shortcut).
 //   * the epilogue never blocks a builder: it runs a full tile behind the MMAs (double-buffered TMEM).
 #include "conv_tc.cuh"
 
@@ -60,26 +61,70 @@ __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
     return r;
 }
 
-// Converts one pair of float4 (8 consecutive channels of one patch row) and stores the row chunk of both planes.
-//   MODE 0: y = x;  1: y = x * sc + sh;  2: SiLU of that.   E4M3: second plane = [A_lo8 x 8 | A_hi8 x 8].
-template <int MODE, bool E4M3>
-__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, const float (&k_sc)[8],
-                                              const float (&k_sh)[8], bool inside, uint32_t dst_hi, uint32_t dst_2,
-                                              float a8_hi, float a8_lo) {
+// Builder pipeline per patch and thread (rows live in a register set v[6][2]):
+//   load_rows   — ONE burst of global loads (12 x 16 bytes in flight per thread) into the set;
+//   touch_rows  — a whole patch later: the first arithmetic on the loaded values, in place (GroupNorm affine
+//                 x * sc + sh, or an exact identity add for raw shortcut operands).  This is where the warp waits
+//                 for the burst — and it runs BEFORE the next burst (into the other set) is issued, with the slot
+//                 wait's spin loop in between so that ptxas cannot reorder the two.  Reason: ptxas puts every one
+//                 of these loads on the same scoreboard; a consumer that waits for "its" loads therefore waits for
+//                 everything in flight on that scoreboard.  The first prefetching version re-issued each row's
+//                 loads right after converting that row and lost a full memory round trip per ROW (1.28 ms for the
+//                 builders alone against 1.11 ms without any prefetch, profiles/conv_r2b.md);
+//   convert_rows — SiLU, (hi, lo) / (hi, e4m3) split, swizzled stores: depends on touch_rows' results only.
+__device__ __forceinline__ void load_rows(float4 (&v)[6][2], const PatchPlan& d) {
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+        if ((d.inb >> u) & 1u) {
+            const float* q = d.src + static_cast<size_t>(u) * d.step;
+            v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
+            v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
+        }
+    }
+}
+
+__device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d, const float* __restrict__ sc,
+                                           const float* __restrict__ sh, float negzero) {
+    float k_sc[8], k_sh[8];
+    if (d.mode != 0 && sc != nullptr) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + d.so));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(sc + d.so + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(sh + d.so));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(sh + d.so + 4));
+        k_sc[0] = a0.x; k_sc[1] = a0.y; k_sc[2] = a0.z; k_sc[3] = a0.w;
+        k_sc[4] = a1.x; k_sc[5] = a1.y; k_sc[6] = a1.z; k_sc[7] = a1.w;
+        k_sh[0] = b0.x; k_sh[1] = b0.y; k_sh[2] = b0.z; k_sh[3] = b0.w;
+        k_sh[4] = b1.x; k_sh[5] = b1.y; k_sh[6] = b1.z; k_sh[7] = b1.w;
+    } else {      // raw operand: x * 1 + (-0) == x exactly (negzero is opaque to the compiler)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { k_sc[e] = 1.0f; k_sh[e] = negzero; }
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+        if ((d.inb >> u) & 1u) {
+            v[u][0].x = fmaf(v[u][0].x, k_sc[0], k_sh[0]); v[u][0].y = fmaf(v[u][0].y, k_sc[1], k_sh[1]);
+            v[u][0].z = fmaf(v[u][0].z, k_sc[2], k_sh[2]); v[u][0].w = fmaf(v[u][0].w, k_sc[3], k_sh[3]);
+            v[u][1].x = fmaf(v[u][1].x, k_sc[4], k_sh[4]); v[u][1].y = fmaf(v[u][1].y, k_sc[5], k_sh[5]);
+            v[u][1].z = fmaf(v[u][1].z, k_sc[6], k_sh[6]); v[u][1].w = fmaf(v[u][1].w, k_sc[7], k_sh[7]);
+        }
+    }
+}
+
+// One pair of float4 (8 consecutive channels of one patch row, affine already applied) -> the row chunk of both
+// planes.  SILU: y = t / (1 + 2^(-t log2 e)).  E4M3: second plane = [A_lo8 x 8 | A_hi8 x 8], else fp16 lo.
+template <bool SILU, bool E4M3>
+__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, uint32_t dst_hi,
+                                              uint32_t dst_2, float a8_hi, float a8_lo) {
     uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
     if (inside) {
         float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (MODE != 0) {
+        if (SILU) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float t = fmaf(y[e], k_sc[e], k_sh[e]);
-                if (MODE == 2) {   // SiLU = t / (1 + 2^(-t log2 e)): ex2.approx.ftz + rcp.approx.ftz, no range fix-ups
-                    float ex, rc;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(t * -1.4426950408889634f));
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
-                    t *= rc;
-                }
-                y[e] = t;
+            for (int e = 0; e < 8; ++e) {   // ex2.approx.ftz + rcp.approx.ftz, no range fix-ups
+                float ex, rc;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(y[e] * -1.4426950408889634f));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+                y[e] *= rc;
             }
         }
         if (E4M3) {
@@ -115,40 +160,16 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
     sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
 }
 
-// Converts the thread's rows of the CURRENT patch out of v[][] into the ring slot at `slot_addr` while the rows of
-// the NEXT patch are loaded into the registers just vacated.
-template <int MODE, bool E4M3>
-__device__ __forceinline__ void build_rows(float4 (&v)[6][2], const PatchPlan& cur, const PatchPlan& nxt, bool have_next,
-                                           const float* __restrict__ sc, const float* __restrict__ sh, uint32_t slot_addr,
-                                           uint32_t r0, uint32_t jchunk, float a8_hi, float a8_lo) {
-    float k_sc[8], k_sh[8];
-    if (MODE != 0) {
-        if (sc != nullptr) {
-            const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + cur.so));
-            const float4 a1 = __ldg(reinterpret_cast<const float4*>(sc + cur.so + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(sh + cur.so));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(sh + cur.so + 4));
-            k_sc[0] = a0.x; k_sc[1] = a0.y; k_sc[2] = a0.z; k_sc[3] = a0.w;
-            k_sc[4] = a1.x; k_sc[5] = a1.y; k_sc[6] = a1.z; k_sc[7] = a1.w;
-            k_sh[0] = b0.x; k_sh[1] = b0.y; k_sh[2] = b0.z; k_sh[3] = b0.w;
-            k_sh[4] = b1.x; k_sh[5] = b1.y; k_sh[6] = b1.z; k_sh[7] = b1.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { k_sc[e] = 1.0f; k_sh[e] = 0.0f; }
-        }
-    }
+template <bool SILU, bool E4M3>
+__device__ __forceinline__ void convert_rows(const float4 (&v)[6][2], const PatchPlan& cur, uint32_t slot_addr,
+                                             uint32_t r0, uint32_t jchunk, float a8_hi, float a8_lo) {
 #pragma unroll
     for (int u = 0; u < 6; ++u) {
         if (u < static_cast<int>(cur.niter)) {
             const uint32_t r = r0 + static_cast<uint32_t>(u) * cur.krows;
             const uint32_t off = r * 128u + ((jchunk ^ (r & 7u)) << 4);
-            convert_store<MODE, E4M3>(v[u][0], v[u][1], k_sc, k_sh, ((cur.inb >> u) & 1u) != 0, slot_addr + off,
+            convert_store<SILU, E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, slot_addr + off,
                                       slot_addr + kPatchPlane + off, a8_hi, a8_lo);
-        }
-        if (have_next && ((nxt.inb >> u) & 1u)) {
-            const float* q = nxt.src + static_cast<size_t>(u) * nxt.step;
-            v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
-            v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
         }
     }
 }
@@ -199,7 +220,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
     const int total_patches = p.kblocks + p.kblocks2;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------------ TMA producer: weight stages
             int bs = 0;
@@ -355,7 +376,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             d.inb = skip ? 0u : inb;
             d.so = static_cast<uint32_t>((g_b0 < p.B ? g_b0 : 0) * (C0 + C1) + c);
             d.second = second;
-            d.mode = second ? 0 : (p.fsc != nullptr ? (p.fact ? 2 : 1) : 1);
+            d.mode = second ? 0 : (p.fact ? 2 : 1);
             if (++g_pi == total_patches) {
                 g_pi = 0;
                 g_item += num_clusters;
@@ -364,39 +385,49 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             }
         };
 
-        float4 v[6][2];
-        PatchPlan cur, nxt;
-        if (g_valid) {
-            next_plan(cur);
-#pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                if ((cur.inb >> u) & 1u) {
-                    const float* q = cur.src + static_cast<size_t>(u) * cur.step;
-                    v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
-                    v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
-                }
-            }
-            int as_ = 0;
-            uint32_t aph = 0;
-            while (true) {
-                const bool have_next = g_valid;
-                if (have_next) next_plan(nxt);
-                const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
-                mbar_wait(&aempty[as_], aph ^ 1u);
-                if (cur.second)
-                    build_rows<0, false>(v, cur, nxt, have_next, nullptr, nullptr, slot, r0, jchunk, 0.f, 0.f);
-                else if (cur.mode == 2)
-                    build_rows<2, FP8>(v, cur, nxt, have_next, p.fsc, p.fsh, slot, r0, jchunk, a8_hi, a8_lo);
-                else
-                    build_rows<1, FP8>(v, cur, nxt, have_next, p.fsc, p.fsh, slot, r0, jchunk, a8_hi, a8_lo);
-                // each builder warp publishes its own share (afull counts the builder warps)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&afull[as_]);
-                if (++as_ == NA) { as_ = 0; aph ^= 1u; }
-                if (!have_next) break;
-                cur = nxt;
-            }
+        // two register sets: while one patch is converted out of set X, the loads of the following patch are in
+        // flight into set Y, and vice versa (see load_rows / touch_rows above for the ordering and why)
+        float4 vx[6][2], vy[6][2];
+        PatchPlan px, py;
+        int as_ = 0;
+        uint32_t aph = 0;
+        const float negzero = -(p.acc_scale * 0.0f);
+        auto wait_slot = [&]() { mbar_wait(&aempty[as_], aph ^ 1u); };
+        auto build = [&](const float4 (&v)[6][2], const PatchPlan& cur) {
+            const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
+            if (cur.second)
+                convert_rows<false, false>(v, cur, slot, r0, jchunk, 0.f, 0.f);
+            else if (cur.mode == 2)
+                convert_rows<true, FP8>(v, cur, slot, r0, jchunk, a8_hi, a8_lo);
+            else
+                convert_rows<false, FP8>(v, cur, slot, r0, jchunk, a8_hi, a8_lo);
+            // each builder warp publishes its own share (afull counts the builder warps)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[as_]);
+            if (++as_ == NA) { as_ = 0; aph ^= 1u; }
+        };
+        bool has_x = g_valid, has_y = false;
+        if (has_x) {
+            next_plan(px);
+            load_rows(vx, px);
+            has_y = g_valid;
+            if (has_y) next_plan(py);
+        }
+        while (has_x) {
+            touch_rows(vx, px, p.fsc, p.fsh, negzero);
+            wait_slot();
+            if (has_y) load_rows(vy, py);
+            build(vx, px);
+            has_x = g_valid;
+            if (has_x) next_plan(px);
+            if (!has_y) break;
+            touch_rows(vy, py, p.fsc, p.fsh, negzero);
+            wait_slot();
+            if (has_x) load_rows(vx, px);
+            build(vy, py);
+            has_y = g_valid;
+            if (has_y) next_plan(py);
         }
     } else {
         // ---------------------------------------------------------------------- epilogue (4 warps)

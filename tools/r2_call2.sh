@@ -2,7 +2,7 @@
 # round-2 call 2: role-split fused conv kernel (conv_fused.cu) vs the previous halo kernel; graded-size parity tests
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > gpurun_out/pytest_gpu_c2.log; tail -4 gpurun_out/pytest_gpu_c2.log
+python -m pytest tests -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_gpu_c2.log; tail -4 gpurun_out/pytest_gpu_c2.log
 L=gpurun_out/conv_modes_c2.log; : > $L
 for d in 0 1 2 4; do echo "v2 debug=$d" >> $L; DSEP_CONV_DEBUG=$d DSEP_FUSEDIN=1 DSEP_STATS=1 DSEP_REPS=20 python tools/profile_conv.py 2>&1 | tail -1 >> $L; done
 echo "v2 passes=3" >> $L; DSEP_PASSES=3 DSEP_FUSEDIN=1 DSEP_STATS=1 DSEP_REPS=20 python tools/profile_conv.py 2>&1 | tail -1 >> $L
