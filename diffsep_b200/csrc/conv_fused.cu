@@ -26,18 +26,25 @@ namespace dsep {
 constexpr int kFThreads = 512;
 constexpr int kFBuilderWarps = 8;
 constexpr int kFEpiWarps = 4;
-constexpr int kFNA = 2;                    // A-patch ring slots
 
-template <int NT>
+// TWO: the CTA pair issues ONE tcgen05.mma.cta_group::2 per step from the leader CTA (M = 256: 128 pixels from each
+// CTA, the weight rows split between the two CTAs' shared memory).  Per SM that halves the weight bytes written by
+// TMA and read by the tensor core — in the 2-unit mode the 1-CTA kernel needs 1152 KB of operand reads + 576 KB of
+// weight fill + 220 KB of builder / epilogue traffic per 128-pixel tile through a 128 B/clk shared-memory pipe:
+// 15.2 k clk against 12.4 k clk of tensor time (measured floor 0.92 ms against 0.75 ms).  With the pair: 864 + 288
+// + 220 KB = 10.7 k clk.  The smaller weight stages also pay for a third patch slot.
+template <int NT, bool TWO>
 struct FusedCfg {
-    static constexpr int kBBytes = NT * 128;                   // one weight plane of a stage (64 channels)
+    static constexpr int kNA = TWO ? 3 : 2;                    // A-patch ring slots
+    static constexpr int kBBytes = NT * 128;                   // one whole weight plane of a stage (64 channels)
+    static constexpr int kBPlane = TWO ? kBBytes / 2 : kBBytes;   // this CTA's share of it
     static constexpr int kAStage = 2 * kPatchPlane;
-    static constexpr int kBStage = 2 * kBBytes;
+    static constexpr int kBStage = 2 * kBPlane;
     static constexpr int kStagingBytes = kFEpiWarps * 32 * 32 * 4;
-    static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes - kFNA * kAStage;
+    static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes - kNA * kAStage;
     static constexpr int kBStagesMax = kAvail / kBStage;
     static constexpr int kBStages = kBStagesMax > 8 ? 8 : kBStagesMax;
-    static constexpr int kRingBytes = kFNA * kAStage + kBStages * kBStage;
+    static constexpr int kRingBytes = kNA * kAStage + kBStages * kBStage;
     static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 512 + 1024;
     static constexpr int kTmemCols = 4 * NT;                   // 2 accumulator stages x (main | correction) x NT
 };
@@ -174,14 +181,15 @@ __device__ __forceinline__ void convert_rows(const float4 (&v)[6][2], const Patc
     }
 }
 
-template <int NT, bool FP8>
+template <int NT, bool FP8, bool TWO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
 conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                   const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                   const ConvParams p) {
-    using Cfg = FusedCfg<NT>;
+    using Cfg = FusedCfg<NT, TWO>;
+    static_assert(!TWO || FP8, "the CTA-pair MMA is implemented for the 2-unit mode only");
     constexpr int NS = Cfg::kBStages;
-    constexpr int NA = kFNA;
+    constexpr int NA = Cfg::kNA;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -206,12 +214,17 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         if (p.kblocks2 > 0) { tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo); }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kFEpiWarps); }
-        for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], kFBuilderWarps); mbar_init(&aempty[i], 1); }
+        // 1-CTA MMAs: each CTA's issuer commits to both CTAs' weight slots (multicast weights).  TWO: the leader's
+        // issuer is the only one; it collects the builder / epilogue warps of both CTAs on ITS barriers.
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TWO ? 1 : 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (TWO ? 2 : 1) * kFEpiWarps); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], (TWO ? 2 : 1) * kFBuilderWarps); mbar_init(&aempty[i], 1); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_alloc_2cta<Cfg::kTmemCols>(tmem_ptr);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // both CTAs' barriers are initialised before any multicast targets them
@@ -228,12 +241,17 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             auto load_weights = [&](const CUtensorMap* whi, const CUtensorMap* wlo, int kcol, int wrow) {
                 mbar_wait(&empty[bs], bph ^ 1u);
                 uint8_t* sb = stage_base + NA * Cfg::kAStage + bs * Cfg::kBStage;
+                const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);      // my half of the weight rows
                 if (p.debug & 2) {
-                    mbar_arrive(&full[bs]);
+                    if (!TWO || rank == 0) mbar_arrive(&full[bs]);
+                } else if constexpr (TWO) {
+                    // each CTA keeps its half of the rows of both planes; everything completes on the leader's barrier
+                    if (rank == 0) mbar_arrive_expect_tx(&full[bs], 2u * Cfg::kBBytes);
+                    tma_load_2d_2sm(sb, whi, &full[bs], kcol, wrow_h);
+                    tma_load_2d_2sm(sb + Cfg::kBPlane, wlo, &full[bs], kcol, wrow_h);
                 } else {
                     // each CTA of the pair fetches half of the rows of both planes and multicasts them to both
                     mbar_arrive_expect_tx(&full[bs], 2u * Cfg::kBBytes);
-                    const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);
                     const int boff = static_cast<int>(rank) * (Cfg::kBBytes / 2);
                     tma_load_2d_mc(sb + boff, whi, &full[bs], kcol, wrow_h, 0x3);
                     tma_load_2d_mc(sb + Cfg::kBBytes + boff, wlo, &full[bs], kcol, wrow_h, 0x3);
@@ -247,13 +265,29 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                     for (int tap = 0; tap < p.taps; ++tap)
                         load_weights(&tm_w_hi, &tm_w_lo, kb * 64, tap * p.Cout_pad + n0);
             }
-        } else if (warp == 1) {
-            // ------------------------------------------------------------------ MMA issuer
+        } else if (warp == 1 && !(TWO && rank != 0)) {
+            // ------------------------------------------------------------------ MMA issuer (TWO: the leader CTA's)
             // the WHOLE warp walks the pipeline convergently and one elected lane issues: barrier addresses,
             // descriptors and the accumulate flag stay in uniform registers (see conv_tc.cu)
             const bool leader = elect_one();
-            constexpr uint32_t idesc_n = umma_idesc_f16(128, NT);
+            constexpr uint32_t idesc_n = umma_idesc_f16(TWO ? 256 : 128, NT);
             constexpr uint32_t idesc_2n = umma_idesc_f16(128, 2 * NT);
+            auto mma16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_flag) {
+                if constexpr (TWO) umma_f16_2cta(d, a, b, idesc, acc_flag);
+                else umma_f16(d, a, b, idesc, acc_flag);
+            };
+            auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_flag) {
+                if constexpr (TWO) umma_e4m3_2cta(d, a, b, idesc, acc_flag);
+                else umma_e4m3(d, a, b, idesc, acc_flag);
+            };
+            auto commit_both = [&](uint64_t* bar) {       // arrive on this barrier in BOTH CTAs
+                if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
+                else umma_commit_mc(bar, 0x3);
+            };
+            auto commit_own = [&](uint64_t* bar) {        // TWO: the follower's roles wait on their own copies
+                if constexpr (TWO) umma_commit_2cta_mc(bar, 0x3);
+                else umma_commit(bar);
+            };
             constexpr uint32_t kHiPatch = ((kPatchW * 128) >> 4) | (1u << 14) | (2u << 29);
             constexpr uint32_t kHiPlain = (1024u >> 4) | (1u << 14) | (2u << 29);
             auto desc = [](uint32_t lo, uint32_t hi) {
@@ -284,15 +318,15 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                                 const uint64_t a_hi = desc(a_word + 2 * k, a_hiword);
                                 const uint64_t a_2 = desc(a_word + (kPatchPlane >> 4) + 2 * k, a_hiword);
                                 const uint64_t b_hi = desc(b_word + 2 * k, kHiPlain);
-                                const uint64_t b_2 = desc(b_word + (Cfg::kBBytes >> 4) + 2 * k, kHiPlain);
+                                const uint64_t b_2 = desc(b_word + (Cfg::kBPlane >> 4) + 2 * k, kHiPlain);
                                 if (FP8) {
-                                    umma_f16(d_tmem, a_hi, b_hi, idesc_n, accumulate);             // hi*hi -> [0, NT)
+                                    mma16(d_tmem, a_hi, b_hi, idesc_n, accumulate);                // hi*hi -> [0, NT)
                                     if (main_kb) {   // [A_lo8 | A_hi8] x [W_hi8 ; W_lo8], K = 32 -> [NT, 2NT)
-                                        umma_e4m3(d_tmem + NT, a_2, b_2, idesc_n, accumulate8);
+                                        mma8(d_tmem + NT, a_2, b_2, idesc_n, accumulate8);
                                         accumulate8 = 1;
                                     } else {         // fp16 shortcut K-block: the two corrections join [0, NT)
-                                        umma_f16(d_tmem, a_hi, b_2, idesc_n, 1);
-                                        umma_f16(d_tmem, a_2, b_hi, idesc_n, 1);
+                                        mma16(d_tmem, a_hi, b_2, idesc_n, 1);
+                                        mma16(d_tmem, a_2, b_hi, idesc_n, 1);
                                     }
                                 } else {             // A_hi x [W_hi ; W_lo] (N = 2NT) and A_lo x W_hi
                                     umma_f16(d_tmem, a_hi, b_hi, idesc_2n, accumulate);
@@ -301,7 +335,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                                 accumulate = 1;
                             }
                         }
-                        umma_commit_mc(&empty[bs], 0x3);      // frees the weight slot in BOTH CTAs
+                        commit_both(&empty[bs]);              // frees the weight slot in BOTH CTAs
                     }
                     __syncwarp();
                     if (++bs == NS) { bs = 0; bph ^= 1u; }
@@ -318,11 +352,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                     } else {
                         issue(sa, kHiPlain, !second);
                     }
-                    if (leader) umma_commit(&aempty[as_]);
+                    if (leader) commit_own(&aempty[as_]);
                     __syncwarp();
                     if (++as_ == NA) { as_ = 0; aph ^= 1u; }
                 }
-                if (leader) umma_commit(&tfull[acc]);
+                if (leader) commit_own(&tfull[acc]);
                 __syncwarp();
             }
         }
@@ -404,7 +438,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             // each builder warp publishes its own share (afull counts the builder warps)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&afull[as_]);
+            if (lane == 0) {
+                if (TWO && rank != 0) mbar_arrive_cluster(&afull[as_], 0);     // the leader's MMA warp waits
+                else mbar_arrive(&afull[as_]);
+            }
             if (++as_ == NA) { as_ = 0; aph ^= 1u; }
         };
         bool has_x = g_valid, has_y = false;
@@ -548,7 +585,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                 if (c == kChunks - 1) {   // TMEM fully drained by this warp: hand the buffer back early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    if (lane == 0) {
+                        if (TWO && rank != 0) mbar_arrive_cluster(&tempty[as], 0);
+                        else mbar_arrive(&tempty[as]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -585,16 +625,19 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // the peer may still multicast into / arrive on this CTA's shared memory
-    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (warp == 2) {
+        if constexpr (TWO) tmem_dealloc_2cta<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
 }
 
-template <int NT, bool FP8>
+template <int NT, bool FP8, bool TWO>
 static int launch_fused(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
-    constexpr int kSmem = FusedCfg<NT>::kSmemBytes;
+    constexpr int kSmem = FusedCfg<NT, TWO>::kSmemBytes;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_fused_kernel<NT, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        attr_err = cudaFuncSetAttribute(conv_fused_kernel<NT, FP8, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     });
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_fused_kernel<%d,%d>): %s", NT, (int)FP8, cudaGetErrorString(attr_err));
@@ -602,13 +645,18 @@ static int launch_fused(const ConvMaps& m, const ConvParams& p, cudaStream_t str
     }
     const int max_clusters = conv_num_sms() / 2;
     const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
-    conv_fused_kernel<NT, FP8><<<grid, kFThreads, kSmem, stream>>>(m.w_hi, m.w_lo, m.w2_hi, m.w2_lo, p);
+    conv_fused_kernel<NT, FP8, TWO><<<grid, kFThreads, kSmem, stream>>>(m.w_hi, m.w_lo, m.w2_hi, m.w2_lo, p);
     return check_launch("conv_fused_kernel");
 }
 
 int launch_conv_fused(const ConvMaps& m, const ConvParams& p, int NT, cudaStream_t stream) {
-    if (p.passes == 2) return NT == 64 ? launch_fused<64, true>(m, p, stream) : launch_fused<128, true>(m, p, stream);
-    return NT == 64 ? launch_fused<64, false>(m, p, stream) : launch_fused<128, false>(m, p, stream);
+    // DSEP_CONV_PAIR=0: 1-CTA MMAs with multicast weights in the 2-unit mode too (A/B timing)
+    static const int pair_env = getenv("DSEP_CONV_PAIR") ? atoi(getenv("DSEP_CONV_PAIR")) : 1;
+    if (p.passes == 2 && pair_env != 0)
+        return NT == 64 ? launch_fused<64, true, true>(m, p, stream) : launch_fused<128, true, true>(m, p, stream);
+    if (p.passes == 2)
+        return NT == 64 ? launch_fused<64, true, false>(m, p, stream) : launch_fused<128, true, false>(m, p, stream);
+    return NT == 64 ? launch_fused<64, false, false>(m, p, stream) : launch_fused<128, false, false>(m, p, stream);
 }
 
 }  // namespace dsep
