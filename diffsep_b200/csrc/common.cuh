@@ -53,18 +53,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a broken pipeline traps (-> CUDA error on the host) instead of hanging the box.
+// Bounded wait: a broken pipeline traps (-> CUDA error on the host) within a few seconds instead of hanging the
+// box.  Each try suspends the warp in hardware for at most 20 us (a 10 ms hint once turned a lost wake-up into an
+// apparent hang of an experimental kernel variant); 2^18 tries ~ 5 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
         asm volatile(
             "{\n\t.reg .pred P;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
+            : "r"(addr), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of polling
             : "memory");
         if (done) return;
     }

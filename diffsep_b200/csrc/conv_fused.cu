@@ -650,8 +650,9 @@ static int launch_fused(const ConvMaps& m, const ConvParams& p, cudaStream_t str
 }
 
 int launch_conv_fused(const ConvMaps& m, const ConvParams& p, int NT, cudaStream_t stream) {
-    // DSEP_CONV_PAIR=0: 1-CTA MMAs with multicast weights in the 2-unit mode too (A/B timing)
-    static const int pair_env = getenv("DSEP_CONV_PAIR") ? atoi(getenv("DSEP_CONV_PAIR")) : 1;
+    // DSEP_CONV_PAIR=1: the cta_group::2 variant (experimental: measured slower than 1-CTA MMAs with multicast
+    // weights — 1.33 vs 1.22 ms on the level-0 conv — and not the default)
+    static const int pair_env = getenv("DSEP_CONV_PAIR") ? atoi(getenv("DSEP_CONV_PAIR")) : 0;
     if (p.passes == 2 && pair_env != 0)
         return NT == 64 ? launch_fused<64, true, true>(m, p, stream) : launch_fused<128, true, true>(m, p, stream);
     if (p.passes == 2)
