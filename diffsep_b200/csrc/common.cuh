@@ -73,6 +73,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+// Polling wait (no suspend hint) for barriers completed by REMOTE arrivals (mapa + mbarrier.arrive from the peer CTA,
+// TMA bytes of the peer landing on this barrier): measured on B200, a warp suspended in try_wait is not woken by such
+// a completion before its time hint expires (a 10 ms hint looked like a hang, 20 us cost 3 tiles per miss).
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

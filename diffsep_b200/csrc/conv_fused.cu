@@ -12,8 +12,8 @@
 // sat in the same instruction stream.  Here:
 //   * 16 warps.  Warpgroup 0: TMA weight producer (warp 0), MMA issuer (warp 1, convergent, descriptors in
 //     uniform registers), TMEM allocator (warp 2).  Warpgroups 1-2: eight BUILDER warps.  Warpgroup 3: four
-//     EPILOGUE warps (one per TMEM lane quarter).  setmaxnreg: 40 / 152 / 152 (128 x 40 + 384 x 152
-//     = 63488 of 65536 registers).
+//     EPILOGUE warps (one per TMEM lane quarter).  setmaxnreg: 40 / 144 / 184 (128 x 40 + 256 x 144 + 128 x 184
+//     = 65536 registers).
 //   * builders prefetch: while patch n is converted and stored out of one register set, the global loads of patch
 //     n + 1 are in flight into a second set (issued in one burst at the start of patch n), so a patch's load latency
 //     overlaps a whole patch of arithmetic — across tile and K-block boundaries.  One code path serves both patch
@@ -84,8 +84,8 @@ __device__ __forceinline__ void load_rows(float4 (&v)[6][2], const PatchPlan& d)
     for (int u = 0; u < 6; ++u) {
         if ((d.inb >> u) & 1u) {
             const float* q = d.src + static_cast<size_t>(u) * d.step;
-            v[u][0] = __ldg(reinterpret_cast<const float4*>(q));
-            v[u][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
+            v[u][0] = ldg_stream(q);
+            v[u][1] = ldg_stream(q + 4);
         }
     }
 }
@@ -298,17 +298,22 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             const uint32_t a_ring = smem_u32(stage_base) >> 4;
             const uint32_t b_ring = smem_u32(stage_base + NA * Cfg::kAStage) >> 4;
             const bool do_mma = !(p.debug & 1);
+            // TWO: these barriers are completed by the peer CTA's arrivals / TMA bytes as well -> poll (see mbar_wait_poll)
+            auto mma_wait = [&](uint64_t* bar, uint32_t parity) {
+                if constexpr (TWO) mbar_wait_poll(bar, parity);
+                else mbar_wait(bar, parity);
+            };
             int bs = 0, as_ = 0;
             uint32_t bph = 0, aph = 0;
             int it = 0;
             for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
                 const int acc = it & 1;
-                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
+                mma_wait(&tempty[acc], ((it >> 1) & 1) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 2 * NT;
                 uint32_t accumulate = 0, accumulate8 = 0;
                 auto issue = [&](uint32_t a_word, uint32_t a_hiword, bool main_kb) {
-                    mbar_wait(&full[bs], bph);
+                    mma_wait(&full[bs], bph);
                     tc_fence_after();
                     const uint32_t b_word = b_ring + bs * (Cfg::kBStage >> 4);
                     if (leader) {
@@ -342,7 +347,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                 };
                 for (int pi = 0; pi < total_patches; ++pi) {
                     const bool second = pi < p.kblocks2;
-                    mbar_wait(&afull[as_], aph);
+                    mma_wait(&afull[as_], aph);
                     tc_fence_after();
                     const uint32_t sa = a_ring + as_ * (Cfg::kAStage >> 4);
                     if (!second && p.taps == 9) {
@@ -362,7 +367,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         }
     } else if (warp < 4 + kFBuilderWarps) {
         // ---------------------------------------------------------------------- patch builders
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         const int wtid = static_cast<int>(threadIdx.x) - 128;
         const uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
         const uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
@@ -468,7 +473,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         }
     } else {
         // ---------------------------------------------------------------------- epilogue (4 warps)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         const int wq = warp & 3;               // TMEM lane quarter == warp_id % 4
         const float crel = FP8 ? p.corr_rel : 1.0f;
         constexpr int kChunks = NT / 32;       // 32-column chunks of the tile, all handled by this warp
@@ -553,7 +558,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         res[i] = (n_ok && ((rowmask >> i) & 1u))
-                                     ? __ldg(reinterpret_cast<const float4*>(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half))
+                                     ? ldg_stream(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half)
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -94,6 +94,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// streaming 16-byte load that does not allocate in L1: with ~210 KB of the SM's 228 KB configured as shared memory
+// the L1 is a few KB, and the activation rows streaming through it (46 KB per patch) kept evicting the per-channel
+// tables (GroupNorm affine, bias, FiLM), whose reloads then cost an L2 round trip per patch (ncu: 12 % of the
+// builders' samples sat on the first use of sc / sh)
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 #if DSEP_FP8_CORR
 // 8 activations -> 16 bytes of the e4m3 correction plane: [A_lo8 x 8 | A_hi8 x 8] (the weight plane holds
 // [W_hi8 x 8 | W_lo8 x 8] at the same bytes, so the K = 32 product sums A_lo*W_hi + A_hi*W_lo)
