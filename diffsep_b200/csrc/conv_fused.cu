@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
 }
 
 // Builder pipeline per patch and thread (rows live in a register set v[6][2]):
-//   load_rows   — ONE burst of global loads (12 x 16 bytes in flight per thread) into the set;
+//   load_rows   — ONE burst of global loads (6 x 32 bytes in flight per thread) into the set;
 //   touch_rows  — a whole patch later: the first arithmetic on the loaded values, in place (GroupNorm affine
 //                 x * sc + sh, or an exact identity add for raw shortcut operands).  This is where the warp waits
 //                 for the burst — and it runs BEFORE the next burst (into the other set) is issued, with the slot
@@ -84,12 +84,14 @@ __device__ __forceinline__ void load_rows(float4 (&v)[6][2], const PatchPlan& d)
     for (int u = 0; u < 6; ++u) {
         if ((d.inb >> u) & 1u) {
             const float* q = d.src + static_cast<size_t>(u) * d.step;
-            v[u][0] = ldg_stream(q);
-            v[u][1] = ldg_stream(q + 4);
+            ldg_stream8(q, v[u][0], v[u][1]);
         }
     }
 }
 
+// mode 2 (SiLU follows): the affine is pre-scaled by c = -log2(e), so v holds u = c * t and convert_store needs no
+// multiply in front of ex2: y = t / (1 + 2^u) = u * rcp(c + c * 2^u).
+constexpr float kNegLog2e = -1.4426950408889634f;
 __device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d, const float* __restrict__ sc,
                                            const float* __restrict__ sh, float negzero) {
     float k_sc[8], k_sh[8];
@@ -106,6 +108,10 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d
 #pragma unroll
         for (int e = 0; e < 8; ++e) { k_sc[e] = 1.0f; k_sh[e] = negzero; }
     }
+    if (d.mode == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { k_sc[e] *= kNegLog2e; k_sh[e] *= kNegLog2e; }
+    }
 #pragma unroll
     for (int u = 0; u < 6; ++u) {
         if ((d.inb >> u) & 1u) {
@@ -118,19 +124,21 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d
 }
 
 // One pair of float4 (8 consecutive channels of one patch row, affine already applied) -> the row chunk of both
-// planes.  SILU: y = t / (1 + 2^(-t log2 e)).  E4M3: second plane = [A_lo8 x 8 | A_hi8 x 8], else fp16 lo.
-template <bool SILU, bool E4M3>
-__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, uint32_t dst_hi,
-                                              uint32_t dst_2, float a8_hi, float a8_lo) {
+// planes.  silu: the values are u = -log2(e) * t and y = t / (1 + 2^u) = u * rcp(c + c 2^u) (ex2.approx.ftz +
+// rcp.approx.ftz, no range fix-ups).  E4M3: second plane = [A_lo8 x 8 | A_hi8 x 8] with A_hi8 converted straight from
+// the packed fp16 pairs (the host passes a8_exp = 0) and A_lo8 = e4m3(lo * a8_lo); else the fp16 lo plane.
+template <bool E4M3>
+__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, bool silu, uint32_t dst_hi,
+                                              uint32_t dst_2, float a8_lo) {
     uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
     if (inside) {
         float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (SILU) {
+        if (silu) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {   // ex2.approx.ftz + rcp.approx.ftz, no range fix-ups
+            for (int e = 0; e < 8; ++e) {
                 float ex, rc;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(y[e] * -1.4426950408889634f));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(y[e]));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(ex, kNegLog2e, kNegLog2e)));
                 y[e] *= rc;
             }
         }
@@ -145,19 +153,8 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
             }
             lo[0] = e4m3x4(l[0], l[1], l[2], l[3]);
             lo[1] = e4m3x4(l[4], l[5], l[6], l[7]);
-            if (a8_hi == 1.0f) {       // A_hi8 straight from the packed fp16 pairs
-                lo[2] = e4m3x2_from_f16x2(hi[0]) | (e4m3x2_from_f16x2(hi[1]) << 16);
-                lo[3] = e4m3x2_from_f16x2(hi[2]) | (e4m3x2_from_f16x2(hi[3]) << 16);
-            } else {
-                float h[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
-                    h[2 * e] = b.x * a8_hi; h[2 * e + 1] = b.y * a8_hi;
-                }
-                lo[2] = e4m3x4(h[0], h[1], h[2], h[3]);
-                lo[3] = e4m3x4(h[4], h[5], h[6], h[7]);
-            }
+            lo[2] = e4m3x2_from_f16x2(hi[0]) | (e4m3x2_from_f16x2(hi[1]) << 16);
+            lo[3] = e4m3x2_from_f16x2(hi[2]) | (e4m3x2_from_f16x2(hi[3]) << 16);
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
@@ -167,16 +164,17 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
     sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
 }
 
-template <bool SILU, bool E4M3>
+template <bool E4M3>
 __device__ __forceinline__ void convert_rows(const float4 (&v)[6][2], const PatchPlan& cur, uint32_t slot_addr,
-                                             uint32_t r0, uint32_t jchunk, float a8_hi, float a8_lo) {
+                                             uint32_t r0, uint32_t jchunk, float a8_lo) {
+    const bool silu = cur.mode == 2;
 #pragma unroll
     for (int u = 0; u < 6; ++u) {
         if (u < static_cast<int>(cur.niter)) {
             const uint32_t r = r0 + static_cast<uint32_t>(u) * cur.krows;
             const uint32_t off = r * 128u + ((jchunk ^ (r & 7u)) << 4);
-            convert_store<SILU, E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, slot_addr + off,
-                                      slot_addr + kPatchPlane + off, a8_hi, a8_lo);
+            convert_store<E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, slot_addr + off,
+                                slot_addr + kPatchPlane + off, a8_lo);
         }
     }
 }
@@ -373,7 +371,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         const uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
         const uint32_t a_ring = smem_u32(stage_base);
         const bool skip = (p.debug & 2) != 0;
-        const float a8_hi = FP8 ? p.a8_hi : 0.f, a8_lo = FP8 ? p.a8_lo : 0.f;
+        const float a8_lo = FP8 ? p.a8_lo : 0.f;         // a8_hi == 1 (the dispatch sends other prescales elsewhere)
 
         // generator of this CTA's patch sequence: tiles in schedule order, per tile the shortcut K-blocks then the
         // main ones (the order the MMA issuer consumes them in)
@@ -434,12 +432,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         auto wait_slot = [&]() { mbar_wait(&aempty[as_], aph ^ 1u); };
         auto build = [&](const float4 (&v)[6][2], const PatchPlan& cur) {
             const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
-            if (cur.second)
-                convert_rows<false, false>(v, cur, slot, r0, jchunk, 0.f, 0.f);
-            else if (cur.mode == 2)
-                convert_rows<true, FP8>(v, cur, slot, r0, jchunk, a8_hi, a8_lo);
-            else
-                convert_rows<false, FP8>(v, cur, slot, r0, jchunk, a8_hi, a8_lo);
+            if (FP8 && !cur.second) convert_rows<true>(v, cur, slot, r0, jchunk, a8_lo);
+            else convert_rows<false>(v, cur, slot, r0, jchunk, 0.f);
             // each builder warp publishes its own share (afull counts the builder warps)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
             __syncwarp();

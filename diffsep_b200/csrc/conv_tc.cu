@@ -1227,7 +1227,8 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
     // Cout >= 64 with the operand built in-kernel: the role-split kernel of conv_fused.cu (DSEP_CONV_V2=0: the
     // previous one-worker-role halo kernel below, kept for A/B timing)
     static const int v2_env = getenv("DSEP_CONV_V2") ? atoi(getenv("DSEP_CONV_V2")) : 1;
-    if (halo && main_fused && NT >= 64 && passes != 1 && v2_env != 0 && !two_env) return launch_conv_fused(m, p, NT, s);
+    if (halo && main_fused && NT >= 64 && passes != 1 && v2_env != 0 && !two_env && (passes != 2 || a8_exp == 0))
+        return launch_conv_fused(m, p, NT, s);
     if (halo && NT == 16) return launch_conv<16, true>(m, p, s);
 #if DSEP_FP8_CORR
     if (passes == 2 && two_env)

@@ -98,6 +98,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // the L1 is a few KB, and the activation rows streaming through it (46 KB per patch) kept evicting the per-channel
 // tables (GroupNorm affine, bias, FiLM), whose reloads then cost an L2 round trip per patch (ncu: 12 % of the
 // builders' samples sat on the first use of sc / sh)
+// 32 bytes (8 channels of one pixel) in ONE 256-bit load: a whole sector per lane.  Two 16-byte loads would each touch
+// half of every sector — harmless with L1 allocation (the second hits), twice the L2 requests without it.
+__device__ __forceinline__ void ldg_stream8(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
