@@ -93,22 +93,37 @@ def cpu_sample(n_evals_N, threads):
     return dt, 1.0 / (dt * NFE / nfe), nfe
 
 
+REFERENCE_BUDGET_S = float(os.environ.get("DSEP_REF_BUDGET_S", "240"))
+
+
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's own path (the oracle; the Python reference cannot
+    travel to the GPU box) on all host cores.  Each step is 1 utterance x n PC steps (corrector + predictor = 2n
+    network evaluations) with n chosen from a calibration evaluation so that warm-up + timed steps fit in
+    DSEP_REF_BUDGET_S (240 s); when the budget allows n = 30 a step IS the whole job of one utterance (no
+    extrapolation), otherwise the value is scaled by 30 / n (the job is n-linear: 60 identical evaluations)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    t_cal, _, nfe_cal = cpu_sample(1, threads)                  # calibration (also warms oneDNN / the allocator up)
+    per_eval = t_cal / nfe_cal
+    n_pc = int(REFERENCE_BUDGET_S / (max(args.steps + args.warmup, 1) * (CORR_STEPS + 1) * per_eval))
+    n_pc = max(1, min(N_STEPS, n_pc))
     for _ in range(args.warmup):
-        cpu_sample(1, threads)
+        cpu_sample(n_pc, threads)
     t0 = time.perf_counter()
     nfe = 0
     for _ in range(args.steps):
-        _, _, n = cpu_sample(1, threads)
+        _, _, n = cpu_sample(n_pc, threads)
         nfe += n
     dt = time.perf_counter() - t0
     utt_s = args.steps / (dt * NFE / (nfe / args.steps)) if dt > 0 else 0.0
+    scale = NFE * args.steps / nfe
     sample = (f"per step: 1 utterance x {nfe // args.steps} of the job's {NFE} score evaluations "
-              f"(N=1 PC step incl. corrector) through the CPU oracle, scaled x{NFE * args.steps // nfe}")
+              f"(N={n_pc} PC steps incl. corrector) through the CPU oracle"
+              + (", the whole job: no extrapolation" if scale == 1 else f", scaled x{scale:g}")
+              + f"; {per_eval:.2f} s per evaluation at calibration")
     line = {
         "impl": "reference", "metric": METRIC, "value": utt_s, "unit": "utt/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,

@@ -22,7 +22,7 @@ _p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
 class SdeParams(C.Structure):
     _fields_ = [("d_lambda", C.c_float), ("sigma_min", C.c_float), ("sigma_max", C.c_float),
-                ("T_end", C.c_float)]
+                ("T_end", C.c_float), ("ndim", C.c_int)]
 
 
 class ConvArgs(C.Structure):
@@ -59,7 +59,7 @@ PROTOTYPES = {
     "dsep_spec_pack": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     "dsep_out_head": [_p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _f, _p, _p],
     "dsep_istft_ola": [_p, _p, _i, _i, _i, _i, _p, _p],
-    "dsep_sde_prior": [C.POINTER(SdeParams), _p, _p, _p, _u64, _u64, _i, _i, _p, _p],
+    "dsep_sde_prior": [C.POINTER(SdeParams), _p, _i, _f, _p, _i, _p, _u64, _u64, _i, _i, _p, _p],
     "dsep_sde_corrector": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
     "dsep_sde_predictor": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _i, _p, _p, _p],
     "dsep_sde_corrector_ald": [C.POINTER(SdeParams), _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],

@@ -10,8 +10,8 @@
 //
 // With A the channel-averaging matrix and Pn = I - A (sdes.py:242-248) every matrix the reference
 // builds is a A + b Pn, so  (a A + b Pn) v = a vbar + b (v - vbar)  with vbar the channel mean:
-// the [B,2,2] / [B,2,2,T] einsums collapse to two FMAs per element.  x is [B, 2, T]; one thread
-// owns VEC consecutive samples of BOTH channels, so the channel mean never leaves registers and
+// the [B,n,n] / [B,n,n,T] einsums collapse to two FMAs per element.  x is [B, ndim, T] (ndim = 2, or 3 for the
+// 3-speaker models); one thread owns VEC consecutive samples of ALL channels, so the channel mean never leaves registers and
 // every access is a coalesced 4*VEC-byte vector.  The reference launches ~8-15 kernels per update
 // (pow, exp, sqrt, einsum, randn_like, axpy ...); here it is one, HBM-bound: 4-5 arrays read,
 // 2 written.
@@ -110,58 +110,107 @@ __device__ __forceinline__ SdeScalars sde_scalars(const dsep_sde_params& p, floa
     return s;
 }
 
-// MODE 0: prior, 1: corrector, 2: predictor.   grid (ceil(T/VEC/256), B)
-template <int MODE, int VEC>
+// (a A + b Pn) applied to the NC channel values v[c] of one sample: a vbar + b (v - vbar)
+template <int NC>
+__device__ __forceinline__ float chan_mean(const float (&v)[NC]) {
+    if (NC == 2) return 0.5f * (v[0] + v[1]);
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) s += v[c];
+    return s * (1.0f / NC);
+}
+template <int NC>
+__device__ __forceinline__ void apply_std(float a, float b, const float (&v)[NC], float (&o)[NC]) {
+    const float m = chan_mean<NC>(v);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) o[c] = a * m + b * (v[c] - m);
+}
+
+// MODE 0: prior, 1: ald2 corrector, 2: predictor, 3: ald corrector.   grid (ceil(T/VEC/256), B).  NC = ndim sources
+// (2, or 3 for the 3-speaker models: every matrix is still a A + b Pn with A = ones(NC, NC) / NC, sdes.py:242-248).
+// MODE 0 only: `flag` = channels of mix (1: broadcast, NC: the true_mean branch of prior_sampling, sdes.py:571-583),
+// coef = factor on the mean (0.5 for a 1-channel mixture and always for MixSDE, :344; 1 for PriorMixSDE's NC-channel
+// branch), sig_ch = channels of sigma_mix (NC when it was computed from an NC-channel input: L = (...)[c,d] sigma[d]).
+template <int MODE, int VEC, int NC>
 __global__ void __launch_bounds__(256)
 sde_update_kernel(const dsep_sde_params p, const float* __restrict__ x, const float* __restrict__ score,
                   const float* __restrict__ mix, const float* __restrict__ tvec,
                   const float* __restrict__ sigma_mix, const float* __restrict__ noise, uint64_t seed,
-                  uint64_t offset, float coef, int flag, int T, float* __restrict__ x_out,
+                  uint64_t offset, float coef, int flag, int sig_ch, int T, float* __restrict__ x_out,
                   float* __restrict__ x_mean) {
     const int b = blockIdx.y;
     const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (t0 >= T) return;
     const SdeScalars sc = sde_scalars(p, MODE == 0 ? p.T_end : tvec[b]);
-    const int64_t e0 = (static_cast<int64_t>(b) * 2) * T + t0, e1 = e0 + T;
-    Vec<VEC> sm;
+    int64_t e[NC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sm.v[i] = 1.0f;
-    if (sigma_mix != nullptr) sm = ldv<VEC>(sigma_mix + static_cast<int64_t>(b) * T + t0);
-    const Vec<VEC> z0 = noise_at<VEC>(noise, e0, seed, offset), z1 = noise_at<VEC>(noise, e1, seed, offset);
-    Vec<VEC> o0, o1, m0, m1;
+    for (int c = 0; c < NC; ++c) e[c] = (static_cast<int64_t>(b) * NC + c) * T + t0;
+    Vec<VEC> sm[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sm[c].v[i] = 1.0f;
+    }
+    if (sigma_mix != nullptr) {
+        if (MODE == 0 && sig_ch == NC) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) sm[c] = ldv<VEC>(sigma_mix + e[c]);
+        } else {
+            sm[0] = ldv<VEC>(sigma_mix + static_cast<int64_t>(b) * T + t0);
+#pragma unroll
+            for (int c = 1; c < NC; ++c) sm[c] = sm[0];
+        }
+    }
+    Vec<VEC> z[NC], o[NC], m[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) z[c] = noise_at<VEC>(noise, e[c], seed, offset);
     if (MODE == 0) {
-        const Vec<VEC> mx = ldv<VEC>(mix + static_cast<int64_t>(b) * T + t0);
+        Vec<VEC> mx[NC];
+        if (flag == NC) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) mx[c] = ldv<VEC>(mix + e[c]);
+        } else {
+            mx[0] = ldv<VEC>(mix + static_cast<int64_t>(b) * T + t0);
+#pragma unroll
+            for (int c = 1; c < NC; ++c) mx[c] = mx[0];
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float zb = 0.5f * (z0.v[i] + z1.v[i]);
-            const float mean = 0.5f * mx.v[i];
-            o0.v[i] = mean + (sc.s1 * zb + sc.s2 * (z0.v[i] - zb)) * sm.v[i];
-            o1.v[i] = mean + (sc.s1 * zb + sc.s2 * (z1.v[i] - zb)) * sm.v[i];
+            float w[NC], l[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) w[c] = z[c].v[i] * sm[c].v[i];      // L = (s1 A + s2 Pn) diag(sigma)
+            apply_std<NC>(sc.s1, sc.s2, w, l);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) o[c].v[i] = coef * mx[c].v[i] + l[c];
         }
-        stv<VEC>(x_out + e0, o0);
-        stv<VEC>(x_out + e1, o1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) stv<VEC>(x_out + e[c], o[c]);
         return;
     }
-    const Vec<VEC> x0 = ldv<VEC>(x + e0), x1 = ldv<VEC>(x + e1);
-    const Vec<VEC> s0 = ldv<VEC>(score + e0), s1 = ldv<VEC>(score + e1);
+    Vec<VEC> xv[NC], sv[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { xv[c] = ldv<VEC>(x + e[c]); sv[c] = ldv<VEC>(score + e[c]); }
     if (MODE == 1) {
         // ald2: x_mean = x + 2 snr^2 L (L s);  x' = x_mean + 2 snr L z        (coef = snr)
         const float c2 = 2.0f * coef * coef, c1 = 2.0f * coef;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float sb = 0.5f * (s0.v[i] + s1.v[i]);
-            float l0 = (sc.s1 * sb + sc.s2 * (s0.v[i] - sb)) * sm.v[i];
-            float l1 = (sc.s1 * sb + sc.s2 * (s1.v[i] - sb)) * sm.v[i];
-            const float lb = 0.5f * (l0 + l1);
-            const float g0 = (sc.s1 * lb + sc.s2 * (l0 - lb)) * sm.v[i];
-            const float g1 = (sc.s1 * lb + sc.s2 * (l1 - lb)) * sm.v[i];
-            const float zb = 0.5f * (z0.v[i] + z1.v[i]);
-            const float n0 = (sc.s1 * zb + sc.s2 * (z0.v[i] - zb)) * sm.v[i];
-            const float n1 = (sc.s1 * zb + sc.s2 * (z1.v[i] - zb)) * sm.v[i];
-            m0.v[i] = x0.v[i] + c2 * g0;
-            m1.v[i] = x1.v[i] + c2 * g1;
-            o0.v[i] = m0.v[i] + c1 * n0;
-            o1.v[i] = m1.v[i] + c1 * n1;
+            const float sg = sm[0].v[i];
+            float a[NC], l[NC], g[NC], n[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a[c] = sv[c].v[i];
+            apply_std<NC>(sc.s1, sc.s2, a, l);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) l[c] *= sg;
+            apply_std<NC>(sc.s1, sc.s2, l, g);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a[c] = z[c].v[i];
+            apply_std<NC>(sc.s1, sc.s2, a, n);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                m[c].v[i] = xv[c].v[i] + c2 * (g[c] * sg);
+                o[c].v[i] = m[c].v[i] + c1 * (n[c] * sg);
+            }
         }
     } else if (MODE == 3) {
         // ald (original annealed Langevin, correctors.py:58-91): std = sqrt of the first-row sum of the
@@ -169,10 +218,11 @@ sde_update_kernel(const dsep_sde_params p, const float* __restrict__ x, const fl
         const float step = 2.0f * (coef * sc.s1) * (coef * sc.s1), nz = sqrtf(2.0f * step);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            m0.v[i] = x0.v[i] + step * s0.v[i];
-            m1.v[i] = x1.v[i] + step * s1.v[i];
-            o0.v[i] = m0.v[i] + nz * z0.v[i];
-            o1.v[i] = m1.v[i] + nz * z1.v[i];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                m[c].v[i] = xv[c].v[i] + step * sv[c].v[i];
+                o[c].v[i] = m[c].v[i] + nz * z[c].v[i];
+            }
         }
     } else {
         // reverse diffusion: f = -lambda (x - xbar) dt, G = g sqrt(dt);  x_mean = x - (f - c G^2 s);
@@ -182,21 +232,24 @@ sde_update_kernel(const dsep_sde_params p, const float* __restrict__ x, const fl
         const float cs = flag ? 0.5f : 1.0f, cz = flag ? 0.0f : 1.0f;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const float xb = 0.5f * (x0.v[i] + x1.v[i]);
-            const float G = sc.g * sm.v[i] * sq;
-            const float f0 = -p.d_lambda * (x0.v[i] - xb) * dt;
-            const float f1 = -p.d_lambda * (x1.v[i] - xb) * dt;
-            m0.v[i] = x0.v[i] - (f0 - cs * G * G * s0.v[i]);
-            m1.v[i] = x1.v[i] - (f1 - cs * G * G * s1.v[i]);
-            o0.v[i] = m0.v[i] + cz * G * z0.v[i];
-            o1.v[i] = m1.v[i] + cz * G * z1.v[i];
+            float a[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a[c] = xv[c].v[i];
+            const float xb = chan_mean<NC>(a);
+            const float G = sc.g * sm[0].v[i] * sq;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float f = -p.d_lambda * (a[c] - xb) * dt;
+                m[c].v[i] = a[c] - (f - cs * G * G * sv[c].v[i]);
+                o[c].v[i] = m[c].v[i] + cz * G * z[c].v[i];
+            }
         }
     }
-    stv<VEC>(x_out + e0, o0);
-    stv<VEC>(x_out + e1, o1);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) stv<VEC>(x_out + e[c], o[c]);
     if (x_mean != nullptr) {
-        stv<VEC>(x_mean + e0, m0);
-        stv<VEC>(x_mean + e1, m1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) stv<VEC>(x_mean + e[c], m[c]);
     }
 }
 
@@ -329,29 +382,42 @@ __global__ void randn_kernel(float* __restrict__ z, int64_t n, uint64_t seed, ui
     }
 }
 
-template <int MODE>
-static int launch_update(const dsep_sde_params* p, const float* x, const float* score, const float* mix,
-                         const float* t, const float* sigma_mix, const float* noise, uint64_t seed,
-                         uint64_t offset, float coef, int flag, int B, int T, float* x_out, float* x_mean,
-                         cudaStream_t s) {
+template <int MODE, int NC>
+static int launch_update_nc(const dsep_sde_params* p, const float* x, const float* score, const float* mix,
+                            const float* t, const float* sigma_mix, const float* noise, uint64_t seed,
+                            uint64_t offset, float coef, int flag, int sig_ch, int B, int T, float* x_out,
+                            float* x_mean, cudaStream_t s) {
     auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool vec = (T % 4 == 0) && aligned(x) && aligned(score) && aligned(mix) && aligned(sigma_mix) &&
                      aligned(noise) && aligned(x_out) && aligned(x_mean);
     if (vec) {
         dim3 grid(ceil_div(T / 4, 256), B);
-        sde_update_kernel<MODE, 4><<<grid, 256, 0, s>>>(*p, x, score, mix, t, sigma_mix, noise, seed, offset,
-                                                        coef, flag, T, x_out, x_mean);
+        sde_update_kernel<MODE, 4, NC><<<grid, 256, 0, s>>>(*p, x, score, mix, t, sigma_mix, noise, seed, offset,
+                                                            coef, flag, sig_ch, T, x_out, x_mean);
     } else {
         dim3 grid(ceil_div(T, 256), B);
-        sde_update_kernel<MODE, 1><<<grid, 256, 0, s>>>(*p, x, score, mix, t, sigma_mix, noise, seed, offset,
-                                                        coef, flag, T, x_out, x_mean);
+        sde_update_kernel<MODE, 1, NC><<<grid, 256, 0, s>>>(*p, x, score, mix, t, sigma_mix, noise, seed, offset,
+                                                            coef, flag, sig_ch, T, x_out, x_mean);
     }
     return check_launch("sde_update_kernel");
+}
+
+template <int MODE>
+static int launch_update(const dsep_sde_params* p, const float* x, const float* score, const float* mix,
+                         const float* t, const float* sigma_mix, const float* noise, uint64_t seed,
+                         uint64_t offset, float coef, int flag, int sig_ch, int B, int T, float* x_out, float* x_mean,
+                         cudaStream_t s) {
+    if (p->ndim == 3)
+        return launch_update_nc<MODE, 3>(p, x, score, mix, t, sigma_mix, noise, seed, offset, coef, flag, sig_ch, B, T,
+                                         x_out, x_mean, s);
+    return launch_update_nc<MODE, 2>(p, x, score, mix, t, sigma_mix, noise, seed, offset, coef, flag, sig_ch, B, T,
+                                     x_out, x_mean, s);
 }
 
 static int check_sde(const char* who, const dsep_sde_params* p, int B, int T) {
     DSEP_REQUIRE(p != nullptr, "%s: null parameters", who);
     DSEP_REQUIRE(p->sigma_min > 0.f && p->sigma_max > p->sigma_min, "%s: need 0 < sigma_min < sigma_max", who);
+    DSEP_REQUIRE(p->ndim == 0 || p->ndim == 2 || p->ndim == 3, "%s: ndim must be 2 or 3 (got %d)", who, p->ndim);
     DSEP_REQUIRE(B > 0 && T > 0 && B <= 65535, "%s: bad shape B=%d T=%d", who, B, T);
     return DSEP_OK;
 }
@@ -360,14 +426,19 @@ static int check_sde(const char* who, const dsep_sde_params* p, int B, int T) {
 
 using namespace dsep;
 
-extern "C" int dsep_sde_prior(const dsep_sde_params* p, const float* mix, const float* sigma_mix,
-                              const float* noise, uint64_t seed, uint64_t offset, int B, int T, float* x,
-                              dsep_stream_t stream) {
+extern "C" int dsep_sde_prior(const dsep_sde_params* p, const float* mix, int mix_channels, float mean_scale,
+                              const float* sigma_mix, int sigma_channels, const float* noise, uint64_t seed,
+                              uint64_t offset, int B, int T, float* x, dsep_stream_t stream) {
     int rc = check_sde("sde_prior", p, B, T);
     if (rc) return rc;
     DSEP_REQUIRE(mix && x, "sde_prior: null pointer");
-    return launch_update<0>(p, nullptr, nullptr, mix, nullptr, sigma_mix, noise, seed, offset, 0.f, 0, B, T, x,
-                            nullptr, (cudaStream_t)stream);
+    const int nc = p->ndim == 3 ? 3 : 2;
+    DSEP_REQUIRE(mix_channels == 1 || mix_channels == nc,
+                 "The input provided to prior_sampling should have 1 channel, or the same as the number of speakers. "
+                 "Found %d channels instead.", mix_channels);
+    DSEP_REQUIRE(sigma_mix == nullptr || sigma_channels == 1 || sigma_channels == nc, "sde_prior: bad sigma_channels");
+    return launch_update<0>(p, nullptr, nullptr, mix, nullptr, sigma_mix, noise, seed, offset, mean_scale, mix_channels,
+                            sigma_channels, B, T, x, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int dsep_sde_corrector(const dsep_sde_params* p, const float* x, const float* score,
@@ -377,7 +448,7 @@ extern "C" int dsep_sde_corrector(const dsep_sde_params* p, const float* x, cons
     int rc = check_sde("sde_corrector", p, B, T);
     if (rc) return rc;
     DSEP_REQUIRE(x && score && t && x_out, "sde_corrector: null pointer");
-    return launch_update<1>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, snr, 0, B, T, x_out, x_mean,
+    return launch_update<1>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, snr, 0, 1, B, T, x_out, x_mean,
                             (cudaStream_t)stream);
 }
 
@@ -389,9 +460,8 @@ extern "C" int dsep_sde_predictor(const dsep_sde_params* p, const float* x, cons
     if (rc) return rc;
     DSEP_REQUIRE(x && score && t && x_out, "sde_predictor: null pointer");
     DSEP_REQUIRE(dt > 0.f, "sde_predictor: dt must be positive");
-    return launch_update<2>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, dt, probability_flow ? 1 : 0, B, T,
-                            x_out, x_mean,
-                            (cudaStream_t)stream);
+    return launch_update<2>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, dt, probability_flow ? 1 : 0, 1, B,
+                            T, x_out, x_mean, (cudaStream_t)stream);
 }
 
 extern "C" int dsep_sde_corrector_ald(const dsep_sde_params* p, const float* x, const float* score,
@@ -401,7 +471,7 @@ extern "C" int dsep_sde_corrector_ald(const dsep_sde_params* p, const float* x, 
     int rc = check_sde("sde_corrector_ald", p, B, T);
     if (rc) return rc;
     DSEP_REQUIRE(x && score && t && x_out, "sde_corrector_ald: null pointer");
-    return launch_update<3>(p, x, score, nullptr, t, nullptr, noise, seed, offset, snr, 0, B, T, x_out, x_mean,
+    return launch_update<3>(p, x, score, nullptr, t, nullptr, noise, seed, offset, snr, 0, 1, B, T, x_out, x_mean,
                             (cudaStream_t)stream);
 }
 

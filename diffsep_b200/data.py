@@ -18,6 +18,31 @@ def max_collator(signals):
     return torch.stack(out), spans
 
 
+def wav_length(path):
+    """number of samples per channel of a wav file, from its header (the data is memory-mapped, not read)"""
+    from scipy.io import wavfile
+    _, data = wavfile.read(path, mmap=True)
+    return int(data.shape[0])
+
+
+def bucket_by_length(lengths, batch_size):
+    """Batches of indices in which every item has the SAME length (no padding), at most ``batch_size`` each, in
+    order of first appearance.  The reference evaluates one utterance at a time (evaluate.py:340-376): normalisation,
+    STFT framing and GroupNorm statistics see only that utterance, so a zero-padded ragged batch would change a short
+    utterance's result; equal-length batches reproduce the batch-of-one results exactly."""
+    order, groups = [], {}
+    for i, n in enumerate(lengths):
+        if n not in groups:
+            groups[n] = []
+            order.append(n)
+        groups[n].append(i)
+    batches = []
+    for n in order:
+        idx = groups[n]
+        batches.extend(idx[k:k + batch_size] for k in range(0, len(idx), batch_size))
+    return batches
+
+
 def uncollate(batch, spans):
     """inverse of max_collator on the time axis: list of [..., T_i]"""
     return [batch[i, ..., front:front + n] for i, (front, n) in enumerate(spans)]

@@ -26,6 +26,17 @@ def ptr(t):
     return t.data_ptr()
 
 
+def use_device(device):
+    """Makes ``device`` (``"cuda:1"``, ``1``, ``torch.device``) the current CUDA device: every kernel launches on
+    ``torch.cuda.current_stream()`` of the CURRENT device, so a model living on cuda:1 while cuda:0 is current
+    would launch on the wrong GPU (the reference CLI honours ``-d`` the same way through ``.to(device)``)."""
+    if not torch.cuda.is_available():
+        return
+    dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+        torch.cuda.set_device(dev)
+
+
 def require_device():
     if not torch.cuda.is_available():
         raise RuntimeError("diffsep_b200 needs a CUDA device (B200, sm_100); no CPU fallback exists")
@@ -207,13 +218,13 @@ def istft_ola(frames_t, window, B, Cc, Fr, T, out):
     return out
 
 
-def sde_params(d_lambda, sigma_min, sigma_max, T_end=1.0):
-    return SdeParams(float(d_lambda), float(sigma_min), float(sigma_max), float(T_end))
+def sde_params(d_lambda, sigma_min, sigma_max, T_end=1.0, ndim=2):
+    return SdeParams(float(d_lambda), float(sigma_min), float(sigma_max), float(T_end), int(ndim))
 
 
-def sde_prior(p, mix, sigma_mix, noise, seed, offset, B, T, x):
-    call("dsep_sde_prior", C.byref(p), ptr(_f32(mix, "mix")), ptr(sigma_mix), ptr(_f32(noise, "noise")), seed,
-         offset, B, T, ptr(x), stream())
+def sde_prior(p, mix, sigma_mix, noise, seed, offset, B, T, x, mix_channels=1, mean_scale=0.5, sigma_channels=1):
+    call("dsep_sde_prior", C.byref(p), ptr(_f32(mix, "mix")), mix_channels, mean_scale, ptr(sigma_mix),
+         sigma_channels, ptr(_f32(noise, "noise")), seed, offset, B, T, ptr(x), stream())
     return x
 
 

@@ -22,27 +22,40 @@ _SDE_TARGETS = {"sdes.sdes.MixSDE": "mix", "sdes.sdes.PriorMixSDE": "priormix",
                 "sdes.MixSDE": "mix", "sdes.PriorMixSDE": "priormix"}
 
 
-def checkpoint_state(ckpt):
+def checkpoint_state(ckpt, no_ema=False):
     """``(config, score-model state_dict)`` of a loaded Lightning ``.ckpt`` / HF ``checkpoint.pt`` dict, with the EMA
-    weights swapped in as the reference does on ``.eval()`` (pl_model.py:650-670).  ``ema.shadow_params`` is a
+    weights swapped in as the reference does on ``.eval()`` (pl_model.py:650-670; ``no_ema=True`` is its
+    ``eval(no_ema=True)``).  ``checkpoint["ema"]`` is ``torch_ema.ExponentialMovingAverage.state_dict()``
+    (``decay``, ``num_updates``, ``shadow_params``, ``collected_params``; pl_model.py:672-673); ``shadow_params`` is a
     list in ``parameters()`` order (output_layer first, then all_modules: ncsnpp.py:105,308 — the order of the
-    ``state_dict`` keys); torch_ema tracks only ``requires_grad`` parameters, so the frozen Fourier ``W`` and the
-    STFT window buffers are not in it."""
+    ``state_dict`` keys).  The reference environment does not pin torch_ema, and its versions differ in what the
+    list holds: <= 0.2 tracks only ``requires_grad`` parameters (the frozen Fourier ``W`` is absent), 0.3 tracks every
+    entry of ``parameters()`` (``W`` included, equal to the raw ``W``).  Both layouts are accepted; any other count
+    is an error — silently evaluating raw weights where the reference evaluates EMA weights is not."""
     config = ckpt.get("hyper_parameters", {}).get("config")
     sd = {k[len("score_model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("score_model.")}
     ema = ckpt.get("ema")
-    if ema and ema.get("shadow_params"):
-        names = [k for k in sd if k.startswith("backbone.") and not k.endswith("all_modules.0.W")]
-        shadow = ema["shadow_params"]
-        if len(shadow) == len(names):
-            for k, v in zip(names, shadow):
-                if tuple(v.shape) != tuple(sd[k].shape):
-                    raise ValueError(f"EMA shadow parameter for {k} has shape {tuple(v.shape)}, "
-                                     f"the state_dict has {tuple(sd[k].shape)}")
-                sd[k] = v
-        else:
-            warnings.warn(f"checkpoint holds {len(shadow)} EMA shadow parameters for {len(names)} trainable "
-                          "tensors: EMA weights NOT applied, using the raw state_dict")
+    if ema is None:
+        warnings.warn("EMA state_dict not found in checkpoint!")       # the reference's message, pl_model.py:647
+        return config, sd
+    if no_ema or not ema.get("shadow_params"):
+        return config, sd
+    shadow = ema["shadow_params"]
+    all_names = [k for k in sd if k.startswith("backbone.")]
+    trainable = [k for k in all_names if not k.endswith("all_modules.0.W")]
+    if len(shadow) == len(trainable):
+        names = trainable
+    elif len(shadow) == len(all_names):
+        names = all_names
+    else:
+        raise ValueError(f"checkpoint holds {len(shadow)} EMA shadow parameters; the score model has "
+                         f"{len(trainable)} trainable / {len(all_names)} parameter tensors (pass no_ema=True to "
+                         "evaluate the raw weights)")
+    for k, v in zip(names, shadow):
+        if tuple(v.shape) != tuple(sd[k].shape):
+            raise ValueError(f"EMA shadow parameter for {k} has shape {tuple(v.shape)}, "
+                             f"the state_dict has {tuple(sd[k].shape)}")
+        sd[k] = v
     return config, sd
 
 
@@ -107,6 +120,7 @@ class DiffSepModel(torch.nn.Module):
         super().__init__()
         cfg = _to_plain(config) if config is not None else DEFAULT_CONFIG
         self.config = _ns(cfg)
+        ops.use_device(device)       # kernels launch on the current device's stream: make `device` current
         m = cfg["model"]
         sm = dict(m["score_model"])
         sm.pop("_target_", None)
@@ -171,11 +185,11 @@ class DiffSepModel(torch.nn.Module):
 
     # ------------------------------------------------------------------ checkpoints
     @classmethod
-    def load_from_checkpoint(cls, path, map_location=None, device="cuda", passes=None, **kwargs):
+    def load_from_checkpoint(cls, path, map_location=None, device="cuda", passes=None, no_ema=False, **kwargs):
         """Reads a Lightning ``.ckpt`` / HF ``checkpoint.pt``: ``hyper_parameters.config``,
         ``state_dict`` (``score_model.*``), and — because the reference swaps EMA weights in on
         ``.eval()`` (pl_model.py:650-670) — ``ema.shadow_params`` in ``parameters()`` order."""
         ckpt = torch.load(path, map_location="cpu", weights_only=False)
-        config, sd = checkpoint_state(ckpt)
+        config, sd = checkpoint_state(ckpt, no_ema=no_ema)
         model = cls(config, device=device, passes=passes, score_state_dict=sd)
         return model

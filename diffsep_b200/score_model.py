@@ -71,11 +71,13 @@ class ScoreModelNCSNpp(torch.nn.Module):
             raise NotImplementedError(f"transform '{transform}' (reference uses 'exponent')")
         if spec_trans_learnable:
             raise NotImplementedError("spec_trans_learnable is a training feature")
+        ops.use_device(device)
         ops.require_device()
         self.num_sources = num_sources
         self.n_fft, self.hop = 510, 128
         self.spec_abs_exponent = float(abs(spec_abs_exponent)) if transform == "exponent" else 1.0
-        self.spec_factor = float(spec_factor)
+        # transform == "none": neither the exponent nor the factor is applied (score_models.py:53-54, 68-69)
+        self.spec_factor = float(spec_factor) if transform == "exponent" else 1.0
         backbone_args = dict(backbone_args or {})
         backbone_args.pop("_target_", None)
         self.nf = int(backbone_args.pop("nf", 128))

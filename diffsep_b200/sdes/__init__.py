@@ -44,6 +44,8 @@ def _make_sampler(predictor_name, corrector_name, sde, score_fn, y, true_mean, d
         cond = true_mean if true_mean is not None else y
         # the mixture spectrogram is constant over the run: let the score model keep it
         cache = getattr(score_fn, "cached_mixture", None)
+        if hasattr(sde, "reset_cache"):
+            sde.reset_cache()          # sigma_mix of a previous mixture must not survive into this run
         with torch.no_grad(), (cache(y) if cache is not None else contextlib.nullcontext()):
             xt = sde.prior_sampling(cond.shape, cond)
             # one host read of the grid: every batch entry shares t (sdes/__init__.py:177-178)

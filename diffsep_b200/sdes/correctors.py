@@ -93,7 +93,10 @@ class LangevinCorrector(Corrector):
 
 @CorrectorRegistry.register("none")
 class NoneCorrector(Corrector):
-    """An empty corrector that does nothing."""
+    """An empty corrector that does nothing.  Deliberate deviation: the reference's returns the 1-tuple ``(x,)``
+    (correctors.py:140-141), which breaks the sampler's ``xt, xt_mean = corrector.update_fn(...)`` unpacking
+    (sdes/__init__.py:179) — its "none" corrector cannot run in its own PC sampler.  Here it returns ``(x, x)``
+    like ``ald2`` with ``n_steps=0`` (what configs[0]'s predictor-only run uses), so the registered name works."""
 
     def __init__(self, *args, **kwargs):
         self.snr = 0

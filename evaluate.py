@@ -8,9 +8,12 @@ scope here).  Results JSON keeps the reference's timing fields: ``nfe``, ``runti
         [--corrector-steps 1] [-s linear|log|revlog] [--save-n K] [--limit M]
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 evaluate.py ...     # files sharded over GPUs
 
-Differences from the reference loop, on purpose: batches of more than one utterance (padded like
-``max_collator``), and ``runtime`` is taken with the device synchronised (the reference's timer has no
-``cuda.synchronize()``, evaluate.py:374-376).
+Differences from the reference loop, on purpose: batches of more than one utterance — by default only utterances
+of the SAME length share a batch (``bucket_by_length``), which reproduces the reference's batch-of-one results;
+``--pad-batches`` instead pads ragged batches like ``max_collator`` (faster on ragged folders, but the zero padding
+enters normalisation, STFT frames and GroupNorm statistics, so short utterances then differ from a batch-of-one
+run) — and ``runtime`` is taken with the device synchronised (the reference's timer has no ``cuda.synchronize()``,
+evaluate.py:374-376).
 """
 from __future__ import annotations
 
@@ -38,7 +41,7 @@ def summarize(results):
 
 def main(argv=None):
     import separate as sep_cli
-    from diffsep_b200.data import load_wav, max_collator, save_wav, uncollate
+    from diffsep_b200.data import bucket_by_length, load_wav, max_collator, save_wav, uncollate, wav_length
     from diffsep_b200.shard import shard_bounds
     import torch.distributed as dist
 
@@ -55,6 +58,9 @@ def main(argv=None):
     ap.add_argument("-s", "--schedule", type=str, default=None)
     ap.add_argument("--save-n", type=int, default=None, help="save wavs of the first K batches only (default: all)")
     ap.add_argument("-l", "--limit", type=int, default=None, help="stop after M batches")
+    ap.add_argument("--pad-batches", action="store_true",
+                    help="batch files in folder order and zero-pad ragged batches (results of padded utterances "
+                         "differ from a batch-of-one run); default: only equal-length utterances share a batch")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -76,11 +82,16 @@ def main(argv=None):
     files = files[lo:hi]
     args.output_dir.mkdir(parents=True, exist_ok=True)
 
+    if args.pad_batches:
+        batches = [list(range(k, min(k + args.batch_size, len(files)))) for k in range(0, len(files), args.batch_size)]
+    else:
+        batches = bucket_by_length([wav_length(f) for f in files], args.batch_size)
     results = []
-    for bidx in range(0, len(files), args.batch_size):
-        if args.limit is not None and bidx // args.batch_size >= args.limit:
+    for bno, idx in enumerate(batches):
+        bidx = bno * args.batch_size
+        if args.limit is not None and bno >= args.limit:
             break
-        names = files[bidx:bidx + args.batch_size]
+        names = [files[i] for i in idx]
         wavs = []
         for f in names:
             w, sr = load_wav(f)

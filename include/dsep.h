@@ -221,20 +221,24 @@ int dsep_istft_ola(const float* frames_t, const float* window, int B, int C, int
                    dsep_stream_t stream);
 
 /* ---- SDE arithmetic -------------------------------------------------------------------------
- * All on x [B,2,T].  t is a device array [B].  sigma_mix [B,T] is NULL for MixSDE and
- * PriorMixSDE._std_sigma_mix(mix) for PriorMixSDE.  noise may be NULL: then N(0,1) samples
- * are drawn in-kernel (Philox4x32-10, Box-Muller) from (seed, offset).
- * prior:      x = 0.5 mix + L(T) z                         (sdes/sdes.py:334-346, 564-587)
+ * All on x [B,ndim,T], ndim = 2 sources or 3 (params.ndim; 0 reads as 2).  t is a device array [B].  sigma_mix
+ * [B,T] is NULL for MixSDE and PriorMixSDE._std_sigma_mix(mix) for PriorMixSDE.  noise may be NULL: then N(0,1)
+ * samples are drawn in-kernel (Philox4x32-10, Box-Muller) from (seed, offset).
+ * prior:      x = mean_scale mix + L(T) z                  (sdes/sdes.py:334-346, 564-587); mix is [B,1,T]
+ *             (mix_channels 1: broadcast over the sources, mean_scale 0.5) or, the true_mean branch, [B,ndim,T]
+ *             (mean_scale 0.5 for MixSDE — its broadcast_to(0.5 y) — and 1 for PriorMixSDE, whose sigma_mix is
+ *             then per source: sigma_channels = ndim, L = (s1 A + s2 Pn) diag(sigma))
  * corrector:  xm = x + 2 snr^2 L L score ; x' = xm + 2 snr L z   (sdes/correctors.py:109-128)
  * predictor:  xm = x + lambda dt (x - mean_c x) + c G^2 score ; x' = xm + G z, G = g(t) sqrt(dt)
  *             (sdes/predictors.py:39-66, sdes/sdes.py:93-107,163-171,275-284); probability_flow: c = 1/2
  *             and no noise (sdes.py:143-152,167-170), else c = 1 */
 typedef struct {
     float d_lambda, sigma_min, sigma_max, T_end;
+    int ndim;
 } dsep_sde_params;
-int dsep_sde_prior(const dsep_sde_params* p, const float* mix, const float* sigma_mix,
-                   const float* noise, uint64_t seed, uint64_t offset, int B, int T, float* x,
-                   dsep_stream_t stream);
+int dsep_sde_prior(const dsep_sde_params* p, const float* mix, int mix_channels, float mean_scale,
+                   const float* sigma_mix, int sigma_channels, const float* noise, uint64_t seed, uint64_t offset,
+                   int B, int T, float* x, dsep_stream_t stream);
 int dsep_sde_corrector(const dsep_sde_params* p, const float* x, const float* score, const float* t,
                        const float* sigma_mix, const float* noise, uint64_t seed, uint64_t offset,
                        float snr, int B, int T, float* x_out, float* x_mean, dsep_stream_t stream);

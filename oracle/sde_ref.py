@@ -69,10 +69,25 @@ def mult_L(p, t, v, mix=None):
 
 
 def prior_sampling(p, mix, z):
-    """x_T = 0.5 mix (broadcast to ndim channels) + L(T) z; sdes.py:334-346 / 564-587."""
+    """x_T = mean + L(T) z; sdes.py:334-346 (MixSDE: mean = 0.5 mix broadcast to TWO channels, hard-coded) /
+    564-587 (PriorMixSDE: mean = 0.5 mix broadcast to ndim for a 1-channel input, the input itself for an
+    ndim-channel one — the sampler's ``true_mean`` — and L = (sqrt(ev1) A + sqrt(ev2) Pn)[c,d] sigma_mix[d],
+    :515-528: sigma enters per INPUT channel d, which for a 1-channel mixture is the plain scaling of mult_L)."""
     t = torch.ones(mix.shape[0], dtype=mix.dtype) * p.T
-    mean = torch.broadcast_to(0.5 * mix, (mix.shape[0], p.ndim, mix.shape[2]))
-    return mean + mult_L(p, t, z, mix)
+    if not p.prior:
+        mean = torch.broadcast_to(0.5 * mix, (mix.shape[0], 2, mix.shape[2]))
+        return mean + mult_L(p, t, z, mix)
+    if mix.shape[1] == p.ndim:
+        mean = mix
+    elif mix.shape[1] == 1:
+        mean = torch.broadcast_to(0.5 * mix, (mix.shape[0], p.ndim, mix.shape[2]))
+    else:
+        raise ValueError("The input provided to prior_sampling should have 1 channel, or the same as the number of "
+                         f"speakers. Found {mix.shape[1]} channels instead.")
+    ev1, ev2 = cov_eigval(p, t)
+    w = z * sigma_mix(p, mix)
+    wbar = w.mean(dim=1, keepdim=True)
+    return mean + ev1.sqrt()[:, None, None] * wbar + ev2.sqrt()[:, None, None] * (w - wbar)
 
 
 def diffusion(p, t, mix=None):
@@ -172,10 +187,11 @@ def timesteps(p, eps, schedule=None, dtype=torch.float32):
 
 
 def pc_sampler(p, score_fn, mix, noises, eps=0.03, snr=0.5, corrector_steps=1,
-               denoise=True, schedule=None, intermediate=False):
-    """sdes/__init__.py:166-190.  ``noises``: flat list in draw order."""
+               denoise=True, schedule=None, intermediate=False, true_mean=None):
+    """sdes/__init__.py:166-190.  ``noises``: flat list in draw order.  ``true_mean`` replaces the mixture in the
+    prior only (:171-174)."""
     noises = list(noises)
-    xt = prior_sampling(p, mix, noises.pop(0))
+    xt = prior_sampling(p, mix if true_mean is None else true_mean, noises.pop(0))
     ts = timesteps(p, eps, schedule, mix.dtype)
     im = []
     xt_mean = xt

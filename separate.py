@@ -71,7 +71,9 @@ def scale_output(mix, sep):
 
 
 def separate(mix, model, sampler_kwargs, device):
-    """mix [1, T] (one channel) -> [1, n_src, T] on the CPU (reference separate.py:81-99)."""
+    """mix [C, T] as loaded from the file -> [1, n_src, T] on the CPU (reference separate.py:81-99).  Like the
+    reference, the whole waveform is passed on: the model takes single-channel mixtures and a multi-channel file is
+    an error there (channel mismatch in the backbone's first conv) and here (ValueError from the score model)."""
     mix = mix.to(device=device, dtype=torch.float32)[None]
     (mix_norm, _), *__ = model.normalize_batch((mix, None))
     sampler = model.get_pc_sampler("reverse_diffusion", "ald2", mix_norm, **sampler_kwargs)
@@ -121,7 +123,7 @@ def main(argv=None):
         if sr != model_sr:
             print(f"Skipping {wavpath.stem} due to mismatched sample rate. "
                   f"This model expects {model_sr} Hz, but the file is {sr} Hz.")
-        sep = separate(waveform[:1], model, sampler_kwargs, device)
+        sep = separate(waveform, model, sampler_kwargs, device)
         for i in range(sep.shape[1]):
             spkr_dir = args.output_dir / f"s{i}"
             spkr_dir.mkdir(parents=True, exist_ok=True)

@@ -51,3 +51,20 @@ RESBLOCK_CASES = [
     ("down", dict(cin=16, cout=16, up=False, down=True), (2, 16, 8, 12)),
     ("up", dict(cin=16, cout=16, up=True, down=False), (2, 16, 4, 6)),
 ]
+
+
+# 3-source / true_mean sampler cases of make_golden_ndim.py: (name, sde, ndim, true_mean channels, corrector steps)
+NDIM_CASES = [("prior3", "priormix", 3, 0, 1), ("prior3_cs2", "priormix", 3, 0, 2),
+              ("prior3_true_mean", "priormix", 3, 3, 1), ("prior2_true_mean", "priormix", 2, 2, 1),
+              ("mix2_true_mean", "mix", 2, 2, 1)]
+NDIM_N, NDIM_B, NDIM_T = 6, 2, 1024
+
+
+def ndim_noises(ndim, cs):
+    g = gen(4242 + ndim)
+    return [torch.randn(NDIM_B, ndim, NDIM_T, generator=g) for _ in range(1 + NDIM_N * (cs + 1))]
+
+
+def ndim_true_mean(ch):
+    g = gen(77 + ch)
+    return 0.4 * torch.randn(NDIM_B, ch, NDIM_T, generator=g)

@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def _run(env_extra):
-    env = dict(os.environ, **env_extra)
+    env = dict(os.environ, DSEP_REF_BUDGET_S="15", **env_extra)     # a short sample: the contract is what is checked
     return subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
                            "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
 

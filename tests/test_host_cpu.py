@@ -89,8 +89,9 @@ def test_registries_and_errors():
     c = sde.copy()
     c.N = 5
     assert sde.N == 30 and c.N == 5 and c.T == 1.0
+    assert sdes.PriorMixSDE(ndim=3, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5).ndim == 3    # 3-speaker models
     with pytest.raises(NotImplementedError):
-        sdes.MixSDE(ndim=3, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5)
+        sdes.MixSDE(ndim=4, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5)
     class OtherSDE(sdes.SDE):
         pass
     with pytest.raises(NotImplementedError, match="not yet supported"):
@@ -197,38 +198,82 @@ def test_wav_io_round_trip(tmp_path):
     assert float((z - x).abs().max()) < 1e-4
 
 
-def test_checkpoint_state_swaps_ema_weights_in():
-    """load_from_checkpoint's host logic (reference pl_model.py:642-670): the `score_model.` prefix is stripped, the
-    EMA shadow list (parameters() order, frozen Fourier W excluded) replaces the raw weights, a count mismatch
-    falls back to the raw weights with a warning, a shape mismatch is an error."""
+def _lightning_checkpoint(raw, ema_sd, ema_names, tmp_path=None):
+    """A checkpoint dict shaped like what the reference writes: Lightning's top-level keys, ``state_dict`` with the
+    ``score_model.`` prefix (+ the STFT window buffers), ``hyper_parameters.config``, and ``ema`` =
+    ``torch_ema.ExponentialMovingAverage.state_dict()`` as stored by ``on_save_checkpoint`` (pl_model.py:672-673)."""
+    from diffsep_b200.pl_model import DEFAULT_CONFIG
+    ckpt = {
+        "epoch": 644, "global_step": 1_000_000, "pytorch-lightning_version": "1.6.4",
+        "state_dict": {**{"score_model." + k: v for k, v in raw.items()}, "loss.dummy_buffer": torch.zeros(1)},
+        "loops": {}, "callbacks": {}, "optimizer_states": [{}], "lr_schedulers": [],
+        "hyper_parameters": {"config": DEFAULT_CONFIG},
+        "ema": {"decay": 0.999, "num_updates": 1_000_000, "shadow_params": [ema_sd[k].clone() for k in ema_names],
+                "collected_params": None},
+    }
+    if tmp_path is not None:                       # through torch.save / torch.load like load_from_checkpoint
+        torch.save(ckpt, tmp_path / "checkpoint.pt")
+        ckpt = torch.load(tmp_path / "checkpoint.pt", map_location="cpu", weights_only=False)
+    return ckpt
+
+
+def test_checkpoint_state_swaps_ema_weights_in(tmp_path):
+    """load_from_checkpoint's host logic (reference pl_model.py:642-673): the `score_model.` prefix is stripped and the
+    EMA shadow list (parameters() order) replaces the raw weights, for BOTH torch_ema layouts — <= 0.2 (only
+    requires_grad parameters: the frozen Fourier W absent) and 0.3 (every parameter, W included).  A count that
+    matches neither is an error (the reference always evaluates EMA weights), as is a shape mismatch; no_ema and a
+    missing `ema` entry give the raw weights (the latter with the reference's warning)."""
     import warnings
     from oracle import weights as ow
     from diffsep_b200.pl_model import DEFAULT_CONFIG, checkpoint_state
     ema_sd = ow.make_score_model_state_dict(nf=32, seed=0)
     raw = ow.make_score_model_state_dict(nf=32, seed=1)
-    names = [k for k in ema_sd if k.startswith("backbone.") and not k.endswith("all_modules.0.W")]
-    ckpt = {"state_dict": {**{"score_model." + k: v for k, v in raw.items()}, "other.module": torch.zeros(1)},
-            "hyper_parameters": {"config": DEFAULT_CONFIG},
-            "ema": {"shadow_params": [ema_sd[k] for k in names], "decay": 0.999}}
-    config, sd = checkpoint_state(ckpt)
-    assert config is DEFAULT_CONFIG and set(sd) == set(raw)
-    assert all(torch.equal(sd[k], ema_sd[k]) for k in names)
     w = "backbone.all_modules.0.W"
-    assert torch.equal(sd[w], raw[w])                      # not tracked by torch_ema: stays raw
-    # no EMA entry: raw weights
-    _, sd2 = checkpoint_state({"state_dict": ckpt["state_dict"]})
-    assert all(torch.equal(sd2[k], raw[k]) for k in names)
-    # wrong count: warn and keep raw
-    bad = dict(ckpt, ema={"shadow_params": ckpt["ema"]["shadow_params"][:-1]})
+    every = [k for k in ema_sd if k.startswith("backbone.")]
+    trainable = [k for k in every if k != w]
+    assert len(every) == len(trainable) + 1
+    # torch_ema <= 0.2 layout
+    ckpt = _lightning_checkpoint(raw, ema_sd, trainable, tmp_path)
+    config, sd = checkpoint_state(ckpt)
+    assert config == DEFAULT_CONFIG and set(sd) == set(raw)
+    assert all(torch.equal(sd[k], ema_sd[k]) for k in trainable)
+    assert torch.equal(sd[w], raw[w])                      # not tracked: stays raw
+    assert torch.equal(sd["stft.window"], raw["stft.window"])
+    # torch_ema 0.3 layout: W is in the list too (equal to the raw W in a real checkpoint; here it shows it is taken)
+    ckpt3 = _lightning_checkpoint(raw, ema_sd, every)
+    _, sd3 = checkpoint_state(ckpt3)
+    assert all(torch.equal(sd3[k], ema_sd[k]) for k in every)
+    # eval(no_ema=True) / no EMA entry: raw weights
+    _, sd_raw = checkpoint_state(ckpt, no_ema=True)
+    assert all(torch.equal(sd_raw[k], raw[k]) for k in every)
     with warnings.catch_warnings(record=True) as rec:
         warnings.simplefilter("always")
-        _, sd3 = checkpoint_state(bad)
-    assert rec and "EMA" in str(rec[0].message) and all(torch.equal(sd3[k], raw[k]) for k in names)
+        _, sd2 = checkpoint_state({"state_dict": ckpt["state_dict"]})
+    assert rec and "EMA state_dict not found" in str(rec[0].message)
+    assert all(torch.equal(sd2[k], raw[k]) for k in every)
+    # a count matching neither layout: error, not a silent fall-back to raw weights
+    bad = dict(ckpt, ema=dict(ckpt["ema"], shadow_params=ckpt["ema"]["shadow_params"][:-1]))
+    with pytest.raises(ValueError, match="EMA shadow parameters"):
+        checkpoint_state(bad)
     # wrong shape: error
     shadow = list(ckpt["ema"]["shadow_params"])
     shadow[3] = torch.zeros(7)
     with pytest.raises(ValueError):
-        checkpoint_state(dict(ckpt, ema={"shadow_params": shadow}))
+        checkpoint_state(dict(ckpt, ema=dict(ckpt["ema"], shadow_params=shadow)))
+
+
+def test_noise_source_restarts_with_the_seed():
+    """torch.manual_seed(s) before two runs in one process gives the same Philox (seed, offset) sequence, as the
+    reference's randn does; a different seed a different key."""
+    from diffsep_b200.sdes.noise import NoiseSource
+    src = NoiseSource()
+    torch.manual_seed(11)
+    a = [src.next((1, 2, 8), "cpu")[1:] for _ in range(3)]
+    torch.manual_seed(11)
+    b = [src.next((1, 2, 8), "cpu")[1:] for _ in range(3)]
+    torch.manual_seed(12)
+    c = [src.next((1, 2, 8), "cpu")[1:] for _ in range(3)]
+    assert a == b and a != c and len({o for _, o in a}) == 3 and {k for k, _ in a} == {11}
 
 
 def test_fp8_correction_entry_point_is_shipped_and_validates(lib):

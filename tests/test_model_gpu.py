@@ -463,6 +463,41 @@ def test_sampler_other_plugins_match_reference_golden(golden, case):
     assert rel_l2(out.cpu(), g[name]) < 1e-5
 
 
+@pytest.mark.parametrize("case", cases.NDIM_CASES, ids=lambda c: c[0])
+def test_three_sources_and_true_mean_prior_match_reference_golden(golden, case):
+    """3-source sampling through PriorMixSDE (ndim = 3) and the sampler's ``true_mean`` prior branch, against the
+    real reference sampler (tests/golden/make_golden_ndim.py): the fused update kernels with NC = 3, per-channel
+    sigma_mix in the prior, MixSDE's 0.5 * true_mean quirk."""
+    from diffsep_b200 import sdes
+    from diffsep_b200.pl_model import normalize_batch
+    name, sde_name, ndim, tm_ch, cs = case
+    g = golden("ndim.npz")
+    (mix, _), _, _ = normalize_batch((cases.batch_mix(cases.NDIM_B, cases.NDIM_T).to(DEV), None))
+    sde = sdes.SDERegistry.get_by_name(sde_name)(ndim=ndim, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5,
+                                                 N=cases.NDIM_N)
+    tm = cases.ndim_true_mean(tm_ch).to(DEV) if tm_ch else None
+    with sdes.injected_noise(cases.ndim_noises(ndim, cs)):
+        out, nfe = sdes.get_pc_sampler("reverse_diffusion", "ald2", sde=sde, score_fn=cases.analytic_score, y=mix,
+                                       true_mean=tm, eps=0.03, snr=0.5, corrector_steps=cs, denoise=True)()
+    torch.cuda.synchronize()
+    assert nfe == cases.NDIM_N * (cs + 1) and tuple(out.shape) == (cases.NDIM_B, ndim, cases.NDIM_T)
+    assert rel_l2(out.cpu(), g[name]) < 1e-5
+
+
+def test_three_source_limits_follow_the_reference():
+    """MixSDE.prior_sampling hard-codes two sources in the reference (sdes.py:344): ndim = 3 constructs but cannot
+    sample; PriorMixSDE rejects inputs with neither 1 nor ndim channels with the reference's message (:579-583)."""
+    from diffsep_b200 import sdes
+    y = torch.zeros(1, 1, 256, device=DEV)
+    with pytest.raises(RuntimeError):
+        sdes.MixSDE(3, 2.0, 0.05, 0.5, N=2).prior_sampling(y.shape, y)
+    with pytest.raises(ValueError, match="should have 1 channel"):
+        y2 = torch.zeros(1, 2, 256, device=DEV)
+        sdes.PriorMixSDE(3, 2.0, 0.05, 0.5, N=2).prior_sampling(y2.shape, y2)
+    with pytest.raises(NotImplementedError):
+        sdes.MixSDE(4, 2.0, 0.05, 0.5)
+
+
 def test_ald_rejects_priormix_like_the_reference():
     from diffsep_b200 import sdes
     sde = sdes.PriorMixSDE(2, 2.0, 0.05, 0.5, N=3)

@@ -177,3 +177,19 @@ def test_sampler_other_plugins(golden, case):
     out = sd.pc_sampler_plugins(p, cases.analytic_score, mix, cases.sampler_noises(2, 1024, 10, cs), predictor=pred,
                                 corrector=corr, corrector_steps=cs, denoise=False)
     assert rel_l2(out, g[name]) < 5e-6
+
+
+@pytest.mark.parametrize("case", cases.NDIM_CASES, ids=lambda c: c[0])
+def test_three_sources_and_true_mean_prior(golden, case):
+    """PriorMixSDE with ndim = 3 (the 3-speaker models) and the sampler's ``true_mean`` prior
+    (an ndim-channel input: mean = the input, sigma_mix per input channel; MixSDE keeps its 0.5 and its two
+    hard-coded channels) vs the real reference sampler (tests/golden/make_golden_ndim.py)."""
+    name, sde_name, ndim, tm_ch, cs = case
+    g = golden("ndim.npz")
+    mix, _, _ = sd.normalize_batch(cases.batch_mix(cases.NDIM_B, cases.NDIM_T))
+    p = sd.MixSDEParams(ndim=ndim, N=cases.NDIM_N, prior=sde_name == "priormix")
+    tm = cases.ndim_true_mean(tm_ch) if tm_ch else None
+    out, nfe = sd.pc_sampler(p, cases.analytic_score, mix, cases.ndim_noises(ndim, cs), corrector_steps=cs,
+                             denoise=True, true_mean=tm)
+    assert nfe == cases.NDIM_N * (cs + 1) and out.shape == (cases.NDIM_B, ndim, cases.NDIM_T)
+    assert rel_l2(out, g[name]) < 5e-6
