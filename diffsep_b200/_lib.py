@@ -69,7 +69,8 @@ PROTOTYPES = {
     "dsep_scale_output": [_p, _p, _i, _i, _i, _p, _p],
     "dsep_randn": [_p, _i64, _u64, _u64, _p],
 }
-OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok", "dsep_conv_kblock", "dsep_has_fp8_corr")
+OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok", "dsep_conv_kblock", "dsep_has_fp8_corr",
+                 "dsep_source_hash")
 
 _lib = None
 
@@ -99,6 +100,7 @@ def load():
     lib.dsep_device_ok.restype = C.c_int
     lib.dsep_conv_kblock.restype = C.c_int
     lib.dsep_has_fp8_corr.restype = C.c_int
+    lib.dsep_source_hash.restype = C.c_char_p
     if lib.dsep_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libdsep.so ABI {lib.dsep_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = lib

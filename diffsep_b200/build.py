@@ -1,7 +1,7 @@
 """Builds ``libdsep.so`` (the C-ABI library of hand-written sm_100a kernels) in-tree with nvcc.
 
 nvcc cross-compiles without a GPU, so this runs in the build container as well as on the B200
-box.  The library is rebuilt only when a source is newer than the binary.
+box.  The library is rebuilt whenever the hash of its sources differs from the one embedded in the binary.
 """
 from __future__ import annotations
 
@@ -31,12 +31,35 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
-def needs_build() -> bool:
+def source_hash() -> str:
+    """sha256 over everything the binary depends on: kernel sources, headers, the C-ABI header and the compiler
+    flags.  The library carries the hash it was built from (``dsep_source_hash()``), so "is this binary the one these
+    sources produce" has an answer that does not depend on file times (a snapshot copy resets those)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dsep.h"]
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def built_hash():
+    """the source hash embedded in the existing libdsep.so (None: no library / an older build without one)"""
     if not LIB.exists():
-        return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dsep.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+        return None
+    import ctypes
+    try:
+        lib = ctypes.CDLL(str(LIB))
+        lib.dsep_source_hash.restype = ctypes.c_char_p
+        return lib.dsep_source_hash().decode()
+    except (OSError, AttributeError):
+        return None
+
+
+def needs_build() -> bool:
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -44,13 +67,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     obj_dir = PKG / "build"
     obj_dir.mkdir(exist_ok=True)
+    digest = source_hash()
     nvcc = _nvcc()
     procs = []
     objs = []
     for src in sources():
         obj = obj_dir / (src.stem + ".o")
         objs.append(str(obj))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, f'-DDSEP_SOURCE_HASH="{digest}"', "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

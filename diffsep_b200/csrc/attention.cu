@@ -172,15 +172,13 @@ extern "C" int dsep_attention(const float* qkv, int B, int S, int C, float scale
     DSEP_REQUIRE(B > 0 && S > 0 && C > 0 && C % 4 == 0, "attention: bad shape");
     const size_t smem = sizeof(float) * (static_cast<size_t>(kQT) * C + static_cast<size_t>(kQT) * S);
     DSEP_REQUIRE(smem <= 200 * 1024, "attention: S=%d too long for the single-pass score buffer", S);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             200 * 1024);
+    if (smem > 48 * 1024) {
+        static PerDeviceAttr attr;
+        const cudaError_t e = set_max_smem_once(attr, attention_kernel, 200 * 1024);
         if (e != cudaSuccess) {
             set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return DSEP_ERR_CUDA;
         }
-        configured = 200 * 1024;
     }
     dim3 grid(ceil_div(S, kQT), B);
     attention_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(qkv, S, C, scale, (__half*)o_hi,

@@ -24,6 +24,24 @@ int check_launch(const char* what);   // cudaGetLastError -> DSEP_ERR_CUDA + mes
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per DEVICE: a process that uses cuda:1 after cuda:0 must set the attribute again there.
+// One slot per device ordinal; benign if two threads race on the same slot (both set the same attribute).
+constexpr int kMaxDevices = 64;
+struct PerDeviceAttr {
+    int state[kMaxDevices] = {};        // 0: not set, 1: set, -1: failed
+    cudaError_t err[kMaxDevices] = {};
+};
+template <typename KernelT>
+static inline cudaError_t set_max_smem_once(PerDeviceAttr& a, KernelT kernel, int bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (a.state[dev] == 0) {
+        a.err[dev] = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        a.state[dev] = a.err[dev] == cudaSuccess ? 1 : -1;
+    }
+    return a.err[dev];
+}
+
 // ---------------------------------------------------------------- PTX wrappers (device)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -655,11 +655,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
 template <int NT, bool FP8, bool TWO>
 static int launch_fused(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
     constexpr int kSmem = FusedCfg<NT, TWO>::kSmemBytes;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_fused_kernel<NT, FP8, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    });
+    static PerDeviceAttr attr;
+    const cudaError_t attr_err = set_max_smem_once(attr, conv_fused_kernel<NT, FP8, TWO>, kSmem);
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_fused_kernel<%d,%d>): %s", NT, (int)FP8, cudaGetErrorString(attr_err));
         return DSEP_ERR_CUDA;

@@ -1046,24 +1046,22 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 }
 
 int conv_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
 }
 
 template <int NT, bool HALO, bool TWO = false>
 static int launch_conv(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
     constexpr int kSmem = HALO ? HaloCfg<NT>::kSmemBytes : ConvCfg<NT>::kSmemBytes;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_tc_kernel<NT, HALO, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    });
+    static PerDeviceAttr attr;
+    const cudaError_t attr_err = set_max_smem_once(attr, conv_tc_kernel<NT, HALO, TWO>, kSmem);
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_tc_kernel<%d,%d>): %s", NT, (int)HALO, cudaGetErrorString(attr_err));
         return DSEP_ERR_CUDA;

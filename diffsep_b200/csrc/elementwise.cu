@@ -465,6 +465,10 @@ using namespace dsep;
 
 extern "C" const char* dsep_last_error(void) { return dsep::g_err; }
 extern "C" int dsep_abi_version(void) { return DSEP_ABI_VERSION; }
+#ifndef DSEP_SOURCE_HASH
+#define DSEP_SOURCE_HASH "unknown"
+#endif
+extern "C" const char* dsep_source_hash(void) { return DSEP_SOURCE_HASH; }
 extern "C" int dsep_device_ok(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -553,15 +557,11 @@ static int launch_fir_tile(const float* x, int B, int H, int W, int C, int group
                            const float* gamma, const float* beta, float eps, void* a_hi, void* a_lo,
                            void* r_hi, void* r_lo, float* y, float a8_hi, float a8_lo, cudaStream_t s) {
     using FT = FirTile<MODE>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fir_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             FT::kSmemBytes);
-        if (e != cudaSuccess) {
-            set_error("fir_resample: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return DSEP_ERR_CUDA;
-        }
-        configured = true;
+    static PerDeviceAttr attr;
+    const cudaError_t e = set_max_smem_once(attr, fir_tile_kernel<MODE>, FT::kSmemBytes);
+    if (e != cudaSuccess) {
+        set_error("fir_resample: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return DSEP_ERR_CUDA;
     }
     const int Ho = MODE == 1 ? H * 2 : H / 2, Wo = MODE == 1 ? W * 2 : W / 2;
     const int tiles_w = ceil_div(Wo, FT::OW), tiles_h = ceil_div(Ho, FT::OH);

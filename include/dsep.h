@@ -37,6 +37,8 @@ typedef void* dsep_stream_t; /* cudaStream_t */
 
 const char* dsep_last_error(void);
 int dsep_abi_version(void);
+/* hash of the sources + compiler flags this binary was built from (diffsep_b200/build.py: source_hash()) */
+const char* dsep_source_hash(void);
 /* 1 if the running device is sm_100 (B200); the product path refuses anything else. */
 int dsep_device_ok(void);
 /* channel granularity of dsep_conv2d_tc's operands (Cin, Cin2 must be multiples of it): 64 */

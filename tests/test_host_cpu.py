@@ -185,6 +185,26 @@ def test_max_collator_matches_reference_semantics():
     assert all(torch.equal(a, b) for a, b in zip(back, sig))
 
 
+def test_equal_length_bucketing_for_the_batch_driver(tmp_path):
+    """evaluate.py's default batching: only utterances of the same length share a batch (the reference evaluates one
+    utterance at a time, evaluate.py:340-376; zero padding would enter normalisation / STFT / GroupNorm)."""
+    from diffsep_b200.data import bucket_by_length, save_wav, wav_length
+    lengths = [800, 640, 800, 800, 640, 1000, 800]
+    batches = bucket_by_length(lengths, 2)
+    assert batches == [[0, 2], [3, 6], [1, 4], [5]]
+    assert all(len({lengths[i] for i in b}) == 1 for b in batches)
+    assert sorted(i for b in batches for i in b) == list(range(len(lengths)))
+    save_wav(tmp_path / "a.wav", torch.zeros(1, 777), 8000)
+    assert wav_length(tmp_path / "a.wav") == 777
+
+
+def test_library_carries_the_hash_of_its_sources(lib):
+    """build() is gated on a hash of the sources + flags, embedded in the binary (not on file times)."""
+    from diffsep_b200 import build as b
+    assert lib.dsep_source_hash().decode() == b.source_hash() == b.built_hash()
+    assert not b.needs_build()
+
+
 def test_wav_io_round_trip(tmp_path):
     import numpy as np
     from scipy.io import wavfile
