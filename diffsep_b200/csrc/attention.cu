@@ -3,6 +3,8 @@
 // plain fp32 kernel: scores for a block of queries live in shared memory (no S x S matrix in
 // HBM, unlike the reference's materialised einsum, layerspp.py:83-87), softmax in fp32,
 // output written directly as (hi, lo) fp16 planes for the NIN_3 tensor-core projection.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dsep {
@@ -166,10 +168,19 @@ film_kernel(const float* __restrict__ temb_act, const float* __restrict__ Wd,
 
 using namespace dsep;
 
+// attention_tc.cu: the tcgen05 flash-style kernel (C a multiple of 64, at most 256)
+int dsep_attention_tc_launch(const float* qkv, int B, int S, int C, float scale, void* o_hi, void* o_lo,
+                             cudaStream_t stream);
+
 extern "C" int dsep_attention(const float* qkv, int B, int S, int C, float scale, void* o_hi, void* o_lo,
                               dsep_stream_t stream) {
     DSEP_REQUIRE(qkv && o_hi && o_lo, "attention: null pointer");
-    DSEP_REQUIRE(B > 0 && S > 0 && C > 0 && C % 4 == 0, "attention: bad shape");
+    DSEP_REQUIRE(B > 0 && S > 0 && C > 0 && C % 4 == 0 && B <= 65535, "attention: bad shape");
+    // DSEP_ATTN_TC=0: the fp32 CUDA-core kernel below (kept for A/B checks and for channel counts the tensor-core
+    // kernel does not tile)
+    static const int tc_env = getenv("DSEP_ATTN_TC") ? atoi(getenv("DSEP_ATTN_TC")) : 1;
+    if (tc_env != 0 && C % 64 == 0 && C <= 256)
+        return dsep_attention_tc_launch(qkv, B, S, C, scale, o_hi, o_lo, (cudaStream_t)stream);
     const size_t smem = sizeof(float) * (static_cast<size_t>(kQT) * C + static_cast<size_t>(kQT) * S);
     DSEP_REQUIRE(smem <= 200 * 1024, "attention: S=%d too long for the single-pass score buffer", S);
     if (smem > 48 * 1024) {

@@ -1,0 +1,260 @@
+// Single-head self-attention of AttnBlockpp (layerspp.py:76-92) on tcgen05 tensor cores, flash-style: the S x S
+// score matrix never exists — not in HBM (the reference materialises it: 1920^2 x 4 B per sample and block at
+// configs[4]) and not in shared memory either.
+//
+//   o[b, i, :] = sum_j softmax_j(scale * q_i . k_j) v_j        q, k, v = the three C-channel slices of qkv [B, S, 3C]
+//
+// One CTA = 128 queries of one batch entry; keys are visited in tiles of 32, twice:
+//   pass 1   S_t = Q K_t^T on the tensor core (M = 128, N = 32, K = C) -> TMEM; thread r owns query row r
+//            (tcgen05.ld 32x32b: TMEM lane = row), so the running row maximum and the rescaled row sum are
+//            thread-local — no shuffles, no shared memory;
+//   pass 2   S_t again, P_t = exp(scale S_t - m_r) / l_r exactly normalised, written as split fp16 planes into
+//            shared memory, O += P_t V_t (M = 128, N = C, K = 32) accumulated in TMEM over all tiles with no
+//            rescaling of O (the price: Q K^T is computed twice; attention is < 0.3 % of the network's FLOPs).
+// fp32-grade arithmetic like the convolutions: every operand is a pair of fp16 planes (hi, lo) and every product the
+// three terms hi*hi + lo*hi + hi*lo accumulated in fp32 (the logits feed an exponential: 11-bit operands would put
+// ~1e-3 on the probabilities).  The operands are split in-kernel from the fp32 qkv tensor and stored in the K-major
+// 128-byte (Q, K: rows of 64 channels) / 64-byte (P, V^T: rows of 32 keys) swizzled layouts the descriptors name;
+// V is transposed on the way in so that P V reads it K-major (keys contiguous).
+// Output: (hi, lo) fp16 planes [B, S, C], the operand of the NIN_3 tensor-core projection.
+#include "common.cuh"
+
+namespace dsep {
+
+constexpr int kAQ = 128;       // queries per CTA (MMA M)
+constexpr int kAK = 32;        // keys per tile
+constexpr int kAThreads = 256;
+
+__device__ __forceinline__ void split2h(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - back.y), "f"(a - back.x));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// rows x C fp32 (row pitch `pitch` floats, rows >= n_valid are zero) -> split planes, C/64 K-blocks of
+// [rows x 128 B] each, 128-byte swizzle.  plane(kb, lo) = base + (kb * 2 + lo) * rows * 128.
+template <int ROWS>
+__device__ __forceinline__ void load_split_rows(const float* __restrict__ src, size_t pitch, int n_valid, int C,
+                                                uint32_t base, int tid) {
+    const int chunks = C >> 3;                      // 8-channel chunks per row
+    for (int idx = tid; idx < ROWS * chunks; idx += kAThreads) {
+        const int row = idx / chunks, ch = idx - row * chunks;
+        uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+        if (row < n_valid) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + row * pitch + ch * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + row * pitch + ch * 8 + 4));
+            split2h(a.x, a.y, hi[0], lo[0]); split2h(a.z, a.w, hi[1], lo[1]);
+            split2h(b.x, b.y, hi[2], lo[2]); split2h(b.z, b.w, hi[3], lo[3]);
+        }
+        const int kb = ch >> 3, j = ch & 7;
+        const uint32_t off = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+        const uint32_t p_hi = base + static_cast<uint32_t>(kb * 2) * (ROWS * 128u);
+        sts128u(p_hi + off, hi[0], hi[1], hi[2], hi[3]);
+        sts128u(p_hi + ROWS * 128u + off, lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// grid (ceil(S / 128), B), 256 threads.  C in {64, 128, 192, 256}.
+__global__ void __launch_bounds__(kAThreads, 1)
+attention_tc_kernel(const float* __restrict__ qkv, int S, int C, float scale, __half* __restrict__ o_hi,
+                    __half* __restrict__ o_lo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KB = C >> 6;                                   // 64-channel K-blocks of the Q K^T contraction
+    // layout: Q planes [KB][2][128 x 128 B] | K planes [KB][2][32 x 128 B] | Vt planes [2][C x 64 B] | P planes [2][128 x 64 B]
+    const uint32_t q_base = smem_u32(smem);
+    const uint32_t k_base = q_base + static_cast<uint32_t>(KB) * 2u * (kAQ * 128u);
+    const uint32_t v_base = k_base + static_cast<uint32_t>(KB) * 2u * (kAK * 128u);
+    const uint32_t p_base = v_base + 2u * static_cast<uint32_t>(C) * 64u;
+    uint8_t* tail = smem + (p_base - q_base) + 2u * (kAQ * 64u);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tail);       // MMA completion
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * kAQ;
+    const int nq = min(kAQ, S - q0);
+    const size_t pitch = static_cast<size_t>(3) * C;
+    const float* base = qkv + static_cast<size_t>(b) * S * pitch;
+
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr);
+    load_split_rows<kAQ>(base + static_cast<size_t>(q0) * pitch, pitch, nq, C, q_base, tid);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_s = *tmem_ptr;            // S tile: columns [0, 32)
+    const uint32_t tmem_o = tmem_s + 32;          // O accumulator: columns [32, 32 + C)
+
+    constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);    // SBO 1024, SWIZZLE_128B
+    constexpr uint32_t kHi64 = (512u >> 4) | (1u << 14) | (4u << 29);      // SBO 512,  SWIZZLE_64B
+    auto desc = [](uint32_t addr, uint32_t hi) {
+        uint64_t d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(addr >> 4), "r"(hi));
+        return d;
+    };
+    const uint32_t idesc_s = umma_idesc_f16(kAQ, kAK);
+    const uint32_t idesc_o = umma_idesc_f16(kAQ, C);
+    uint32_t phase = 0;
+    const int n_tiles = (S + kAK - 1) / kAK;
+    const float sl2 = scale * 1.4426950408889634f;           // logits in base-2 units: exp(x) = 2^(x log2 e)
+    float m_run = -INFINITY, l_run = 0.0f;                   // thread = query row (warps 0-3)
+
+    // S_t = Q K_t^T: three products per K = 16 step
+    auto issue_qk = [&]() {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t qh = q_base + static_cast<uint32_t>(kb * 2) * (kAQ * 128u), ql = qh + kAQ * 128u;
+            const uint32_t kh = k_base + static_cast<uint32_t>(kb * 2) * (kAK * 128u), kl = kh + kAK * 128u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                umma_f16(tmem_s, desc(qh + k * 32, kHi128), desc(kh + k * 32, kHi128), idesc_s, acc);
+                umma_f16(tmem_s, desc(ql + k * 32, kHi128), desc(kh + k * 32, kHi128), idesc_s, 1);
+                umma_f16(tmem_s, desc(qh + k * 32, kHi128), desc(kl + k * 32, kHi128), idesc_s, 1);
+                acc = 1;
+            }
+        }
+        umma_commit(bar);
+    };
+
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int t = 0; t < n_tiles; ++t) {
+            const int j0 = t * kAK;
+            const int nk = min(kAK, S - j0);
+            // ---- operands of this tile: K rows (split, 128B-swizzled); pass 2 also V^T (split, 64B-swizzled)
+            load_split_rows<kAK>(base + static_cast<size_t>(j0) * pitch + C, pitch, nk, C, k_base, tid);
+            if (pass == 1) {
+                // thread <-> channel d: 32 keys of V[:, d] -> row d of V^T (4 chunks of 8 keys)
+                for (int d = tid; d < C; d += kAThreads) {
+                    const float* vcol = base + static_cast<size_t>(j0) * pitch + 2 * C + d;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = (c * 8 + i < nk) ? __ldg(vcol + (c * 8 + i) * pitch) : 0.0f;
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split2h(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                        const uint32_t off = static_cast<uint32_t>(d) * 64u + (static_cast<uint32_t>(c ^ ((d >> 1) & 3)) << 4);
+                        sts128u(v_base + off, hi[0], hi[1], hi[2], hi[3]);
+                        sts128u(v_base + static_cast<uint32_t>(C) * 64u + off, lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) { tc_fence_after(); issue_qk(); }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            if (warp < 4) {
+                uint32_t sv[32];
+                tmem_ld_32x32(tmem_s + (static_cast<uint32_t>(warp * 32) << 16), sv);
+                tmem_ld_wait();
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x = (j < nk) ? __uint_as_float(sv[j]) * sl2 : -INFINITY;    // padded keys: p = 0
+                    sv[j] = __float_as_uint(x);
+                    mx = fmaxf(mx, x);
+                }
+                if (pass == 0) {
+                    const float m_new = fmaxf(m_run, mx);
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum += exp2f(__uint_as_float(sv[j]) - m_new);
+                    l_run = l_run * exp2f(m_run - m_new) + sum;
+                    m_run = m_new;
+                } else {
+                    const float inv = 1.0f / l_run;
+                    const int row = warp * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float p0 = exp2f(__uint_as_float(sv[c * 8 + 2 * i]) - m_run) * inv;
+                            const float p1 = exp2f(__uint_as_float(sv[c * 8 + 2 * i + 1]) - m_run) * inv;
+                            split2h(p0, p1, hi[i], lo[i]);
+                        }
+                        const uint32_t off = static_cast<uint32_t>(row) * 64u + (static_cast<uint32_t>(c ^ ((row >> 1) & 3)) << 4);
+                        sts128u(p_base + off, hi[0], hi[1], hi[2], hi[3]);
+                        sts128u(p_base + kAQ * 64u + off, lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            if (pass == 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t ph = p_base, pl = p_base + kAQ * 64u;
+                    const uint32_t vh = v_base, vl = v_base + static_cast<uint32_t>(C) * 64u;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {           // 32 keys = two K = 16 steps
+                        umma_f16(tmem_o, desc(ph + k * 32, kHi64), desc(vh + k * 32, kHi64), idesc_o, (t | k) ? 1u : 0u);
+                        umma_f16(tmem_o, desc(pl + k * 32, kHi64), desc(vh + k * 32, kHi64), idesc_o, 1);
+                        umma_f16(tmem_o, desc(ph + k * 32, kHi64), desc(vl + k * 32, kHi64), idesc_o, 1);
+                    }
+                    umma_commit(bar);
+                }
+                mbar_wait(bar, phase);          // P / V^T / K buffers are free again, S tile may be overwritten
+                phase ^= 1u;
+                tc_fence_after();
+            } else {
+                tc_fence_before();
+                __syncthreads();                // every row has read its S tile before the next Q K^T overwrites it
+            }
+        }
+    }
+
+    // ---- O [128 x C] -> split fp16 planes [B, S, C]; thread = query row, 32 columns at a time
+    if (warp < 4) {
+        const int row = warp * 32 + lane;
+        const size_t off = (static_cast<size_t>(b) * S + q0 + row) * C;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tmem_o + (static_cast<uint32_t>(warp * 32) << 16) + c0, ov);
+            tmem_ld_wait();
+            if (row < nq) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        split2h(__uint_as_float(ov[c * 8 + 2 * i]), __uint_as_float(ov[c * 8 + 2 * i + 1]), hi[i], lo[i]);
+                    *reinterpret_cast<uint4*>(o_hi + off + c0 + c * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(o_lo + off + c0 + c * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_s);
+}
+
+}  // namespace dsep
+
+using namespace dsep;
+
+// host side of dsep_attention's tensor-core path (attention.cu dispatches here)
+int dsep_attention_tc_launch(const float* qkv, int B, int S, int C, float scale, void* o_hi, void* o_lo,
+                             cudaStream_t stream) {
+    const int KB = C / 64;
+    const size_t smem = static_cast<size_t>(KB) * 2 * (kAQ * 128) + static_cast<size_t>(KB) * 2 * (kAK * 128) +
+                        2 * static_cast<size_t>(C) * 64 + 2 * (kAQ * 64) + 64 + 1024;
+    static PerDeviceAttr attr;
+    const cudaError_t e = set_max_smem_once(attr, attention_tc_kernel, 227 * 1024);
+    if (e != cudaSuccess) {
+        set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return DSEP_ERR_CUDA;
+    }
+    dim3 grid(ceil_div(S, kAQ), B);
+    attention_tc_kernel<<<grid, kAThreads, smem, stream>>>(qkv, S, C, scale, (__half*)o_hi, (__half*)o_lo);
+    return check_launch("attention_tc_kernel");
+}

@@ -173,7 +173,10 @@ int dsep_add(const float* a, const float* b, float* y, int64_t n, dsep_stream_t 
 
 /* ---- attention ---------------------------------------------------------------------------
  * qkv fp32 [B,S,3C] (q | k | v per token); o = softmax(q k^T * scale) v written as split planes
- * [B,S,C].  Replaces the two einsums + softmax of AttnBlockpp.forward (layerspp.py:83-88). */
+ * [B,S,C].  Replaces the two einsums + softmax of AttnBlockpp.forward (layerspp.py:83-88).
+ * C a multiple of 64 up to 256 (every NCSN++ width on this path): flash-style on tcgen05 — Q K^T and P V as
+ * three fp16 products each with TMEM accumulators, 128 queries per CTA, keys in tiles of 32, the S x S matrix
+ * never stored anywhere (csrc/attention_tc.cu); other widths: an fp32 CUDA-core kernel. */
 int dsep_attention(const float* qkv, int B, int S, int C, float scale, void* o_hi, void* o_lo,
                    dsep_stream_t stream);
 

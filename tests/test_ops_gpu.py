@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 import cases
-from conftest import rel_l2
+from conftest import ROOT, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -495,19 +495,45 @@ def test_combine():
     assert rel_l2(out.cpu(), ref) < 1e-6
 
 
-@pytest.mark.parametrize("S", [16, 256, 120])
-def test_attention(S):
+@pytest.mark.parametrize("shape", [(2, 16, 128), (2, 256, 128), (2, 120, 128), (3, 256, 256), (2, 1920, 256),
+                                   (1, 200, 64), (2, 512, 256)], ids=lambda s: "x".join(map(str, s)))
+def test_attention(shape):
+    """softmax(q k^T / sqrt(C)) v of AttnBlockpp (layerspp.py:83-88) on the tcgen05 flash-style kernel vs float64:
+    the mid-block token counts (16, 120), the 16 x W/16 levels of configs[1] / [3] / [4] (256, 512, 1920 tokens at
+    C = 256 = 2 nf for nf = 128), partial query blocks and partial key tiles (120, 200), logits with a wide spread."""
     ops = _ops()
-    g = cases.gen(S)
-    B, C = 2, 128
+    B, S, C = shape
+    g = cases.gen(S + C)
     qkv = torch.randn(B, S, 3 * C, generator=g)
+    qkv[:, :, :C] *= 2.0            # sharper softmax: the row maximum matters
     q, k, v = qkv.double().split(C, dim=-1)
     w = torch.softmax(q @ k.transpose(1, 2) * C ** -0.5, dim=-1)
     ref = w @ v
     o = ops.Split.empty((B, S, C), DEV)
+    o.hi.fill_(float("nan")); o.lo.fill_(float("nan"))
     ops.attention(qkv.to(DEV), B, S, C, C ** -0.5, o)
     torch.cuda.synchronize()
-    assert rel_l2((o.hi.float() + o.lo.float()).cpu(), ref) < 2e-6
+    assert rel_l2((o.hi.float() + o.lo.float()).cpu(), ref) < 3e-6
+
+
+def test_attention_tensor_core_kernel_equals_cuda_core_kernel():
+    """the two kernels behind dsep_attention (DSEP_ATTN_TC=0 selects the fp32 CUDA-core one) agree to fp32 rounding"""
+    import subprocess, sys, os
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import cases; from diffsep_b200 import ops\n"
+        "g = cases.gen(3); qkv = torch.randn(2, 256, 768, generator=g).cuda()\n"
+        "o = ops.Split.empty((2, 256, 256), 'cuda'); ops.attention(qkv, 2, 256, 256, 256 ** -0.5, o)\n"
+        "torch.cuda.synchronize(); torch.save((o.hi.float() + o.lo.float()).cpu(), sys.argv[1])\n"
+    ) % (str(ROOT), str(ROOT / "tests" / "golden"))
+    outs = []
+    for tc in ("1", "0"):
+        path = f"/tmp/dsep_attn_{tc}.pt"
+        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, DSEP_ATTN_TC=tc),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(torch.load(path))
+    assert rel_l2(outs[0], outs[1]) < 3e-6
 
 
 def test_time_embedding_and_film():
