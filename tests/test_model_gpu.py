@@ -406,8 +406,9 @@ def test_minibatch_sampler_equals_full_batch():
 
 
 def test_evaluate_batch_driver(tmp_path):
-    """evaluate.py: ragged batch padded like max_collator, per-batch nfe / runtime / len_s JSON
-    (reference evaluate.py:394-406), wavs cropped back to each utterance's length."""
+    """evaluate.py: per-batch nfe / runtime / len_s JSON (reference evaluate.py:394-406), wavs of each utterance's own
+    length.  Default batching puts only equal-length utterances together (batch-of-one results, like the reference's
+    loop); --pad-batches pads ragged batches like max_collator and crops the estimates back."""
     import copy, json, subprocess, sys
     from pathlib import Path
     import numpy as np
@@ -421,23 +422,32 @@ def test_evaluate_batch_driver(tmp_path):
     torch.save({"state_dict": {"score_model." + k: v for k, v in sd_.items()}, "hyper_parameters": {"config": cfg}},
                tmp_path / "ckpt.pt")
     (tmp_path / "in").mkdir()
-    lens = [6000, 8000, 7000]
+    lens = [6000, 8000, 6000, 7000]
     for i, n in enumerate(lens):
         wavfile.write(tmp_path / "in" / f"u{i}.wav", 8000, (cases.synthetic_mix(i, n)[0] * 0.5).numpy().astype(np.float32))
-    r = subprocess.run([sys.executable, str(root / "evaluate.py"), str(tmp_path / "in"), str(tmp_path / "out"),
-                        "--model", str(tmp_path / "ckpt.pt"), "-N", "2", "--batch-size", "2"],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout + r.stderr
-    res = json.loads((tmp_path / "out" / "results.json").read_text())
-    assert [len(b["files"]) for b in res] == [2, 1]
-    assert all(b["nfe"] == 4 and b["runtime"] > 0 for b in res)
-    assert res[0]["len_s"] == [0.75, 1.0] and res[1]["len_s"] == [0.875]
-    summ = json.loads((tmp_path / "out" / "results_summary.json").read_text())
-    assert summ["utterances"] == 3 and summ["utt_per_s"] > 0
-    for i, n in enumerate(lens):
-        for s in (0, 1):
-            sr_, data = wavfile.read(tmp_path / "out" / f"s{s}" / f"u{i}.wav")
-            assert sr_ == 8000 and data.shape == (n,) and np.isfinite(data).all()
+
+    def run(out, *extra):
+        r = subprocess.run([sys.executable, str(root / "evaluate.py"), str(tmp_path / "in"), str(tmp_path / out),
+                            "--model", str(tmp_path / "ckpt.pt"), "-N", "2", "--batch-size", "2", *extra],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        res = json.loads((tmp_path / out / "results.json").read_text())
+        assert all(b["nfe"] == 4 and b["runtime"] > 0 for b in res)
+        summ = json.loads((tmp_path / out / "results_summary.json").read_text())
+        assert summ["utterances"] == len(lens) and summ["utt_per_s"] > 0
+        wavs = {}
+        for i, n in enumerate(lens):
+            for s in (0, 1):
+                sr_, data = wavfile.read(tmp_path / out / f"s{s}" / f"u{i}.wav")
+                assert sr_ == 8000 and data.shape == (n,) and np.isfinite(data).all()
+                wavs[i, s] = data
+        return res, wavs
+
+    res, _ = run("out")                                       # equal-length buckets: {u0, u2}, {u1}, {u3}
+    assert [b["files"] for b in res] == [["u0.wav", "u2.wav"], ["u1.wav"], ["u3.wav"]]
+    assert res[0]["len_s"] == [0.75, 0.75] and res[1]["len_s"] == [1.0] and res[2]["len_s"] == [0.875]
+    res_p, _ = run("out_pad", "--pad-batches")                # folder order, padded: {u0, u1}, {u2, u3}
+    assert [len(b["files"]) for b in res_p] == [2, 2] and res_p[0]["len_s"] == [0.75, 1.0]
 
 
 @pytest.mark.parametrize("case", [("em_ald2", "euler_maruyama", "ald2", "mix", 1, False),

@@ -513,7 +513,8 @@ def test_attention(shape):
     o.hi.fill_(float("nan")); o.lo.fill_(float("nan"))
     ops.attention(qkv.to(DEV), B, S, C, C ** -0.5, o)
     torch.cuda.synchronize()
-    assert rel_l2((o.hi.float() + o.lo.float()).cpu(), ref) < 3e-6
+    # fp32 accumulation (truncating in the tensor core) over up to 1920 keys and 256 channels
+    assert rel_l2((o.hi.float() + o.lo.float()).cpu(), ref) < 1e-5
 
 
 def test_attention_tensor_core_kernel_equals_cuda_core_kernel():
@@ -533,7 +534,7 @@ def test_attention_tensor_core_kernel_equals_cuda_core_kernel():
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append(torch.load(path))
-    assert rel_l2(outs[0], outs[1]) < 3e-6
+    assert rel_l2(outs[0], outs[1]) < 1e-5
 
 
 def test_time_embedding_and_film():
