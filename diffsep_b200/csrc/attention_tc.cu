@@ -169,7 +169,10 @@ attention_tc_kernel(const float* __restrict__ qkv, int S, int C, float scale, __
                     l_run = l_run * exp2f(m_run - m_new) + sum;
                     m_run = m_new;
                 } else {
-                    const float inv = 1.0f / l_run;
+                    // probabilities enter the fp16 planes scaled by 2^10 (undone on the way out, exactly): with 1920
+                    // keys most of them are below fp16's normal range (6e-5), where the (hi, lo) pair no longer
+                    // carries 22 bits — measured 3e-5 on the output at S = 1920 without the scale
+                    const float inv = 1024.0f / l_run;
                     const int row = warp * 32 + lane;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -226,7 +229,8 @@ attention_tc_kernel(const float* __restrict__ qkv, int S, int C, float scale, __
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        split2h(__uint_as_float(ov[c * 8 + 2 * i]), __uint_as_float(ov[c * 8 + 2 * i + 1]), hi[i], lo[i]);
+                        split2h(__uint_as_float(ov[c * 8 + 2 * i]) * (1.0f / 1024.0f),
+                                __uint_as_float(ov[c * 8 + 2 * i + 1]) * (1.0f / 1024.0f), hi[i], lo[i]);
                     *reinterpret_cast<uint4*>(o_hi + off + c0 + c * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(o_lo + off + c0 + c * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
