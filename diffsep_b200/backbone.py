@@ -295,14 +295,24 @@ class NCSNppB200:
         if (B, W) not in keep:
             self._plans.pop((B, W), None)
 
-    def __call__(self, x_planes: Split, x_pyramid, t):
+    def film_rows(self, ts):
+        """FiLM rows [len(ts), R] of the given times (one embedding-MLP launch + one stacked Dense_0 launch)."""
+        n = len(ts)
+        t = torch.tensor(list(ts), dtype=torch.float32, device=self.device)
+        temb = torch.empty(n, self.temb_dim, device=self.device, dtype=torch.float32)
+        out = torch.empty(n, self._film_rows, device=self.device, dtype=torch.float32)
+        ops.time_embedding(t, self.Wf, self.t_w1, self.t_b1, self.t_w2, self.t_b2, n, self.nf, temb)
+        ops.film(temb, self.dense_w, self.dense_b, n, self.temb_dim, self._film_rows, out)
+        return out
+
+    def __call__(self, x_planes: Split, x_pyramid, t, uniform=False):
         """x_planes: split [B,256,W,conv_in.cin_pad] network input (2x-1 applied, channels >= ch_in zero);
         x_pyramid: the same input as fp32 [B,256,W,ch_in]; t: [B].  Returns the output pyramid
         [B,256,W,ch_in] fp32 (before the /t scaling and the output 1x1 conv, which
         ``dsep_out_head`` fuses with the spectrogram decompression)."""
         B, H, W, _ = x_pyramid.shape
         assert H == 256 and W % 64 == 0
-        return self.plan(B, W).run(x_planes, x_pyramid, t)
+        return self.plan(B, W).run(x_planes, x_pyramid, t, uniform=uniform)
 
 
 class Act:
@@ -336,6 +346,7 @@ class _Plan:
         dev = net.device
         self.temb_act = torch.empty(B, net.temb_dim, device=dev, dtype=torch.float32)
         self.film = torch.empty(B, net._film_rows, device=dev, dtype=torch.float32)
+        self.film_stride = net._film_rows    # 0 while every batch entry shares one time: row 0 serves them all
         self.x_planes = None     # bound at run time
         self.x_pyramid = None
         self._stat_chunks, self._stat_used = [], self.STATS_CHUNK
@@ -367,21 +378,21 @@ class _Plan:
               a2=None, stats=None, e4m3=False):
         """e4m3: ``a`` holds (fp16 hi, e4m3 correction) planes (fir_resample with a8_exp) -> passes = 2."""
         net, B = self.net, self.B
-        film_v, stride = None, 0
-        if film is not None:
-            film_v, stride = self.film[:, film:], self.film.shape[1]
+        film_v, has_film = None, film is not None
+        if has_film:
+            film_v = self.film[:, film:]
         w2 = cw.planes2 if a2 is not None else None
         cin2 = cw.cin2_pad if a2 is not None else 0
         if e4m3:
             w8 = cw.planes8()
             self.steps.append(lambda: ops.conv2d_tc(
                 a, B, H, W, cin_pad, w8, cw.cout_pad, cw.ksize, out, cout_store, bias=cw.bias, film=film_v,
-                film_stride=stride, residual=residual, scale=scale, acc_scale=cw.acc_scale, passes=2, a2=a2,
+                film_stride=self.film_stride if has_film else 0, residual=residual, scale=scale, acc_scale=cw.acc_scale, passes=2, a2=a2,
                 Cin2=cin2, w2=w2, stats=stats, corr_rel=cw.corr_rel, a8_exp=cw.A8_EXP))
             return
         self.steps.append(lambda: ops.conv2d_tc(
             a() if callable(a) else a, B, H, W, cin_pad, cw.planes, cw.cout_pad, cw.ksize, out, cout_store,
-            bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
+            bias=cw.bias, film=film_v, film_stride=self.film_stride if has_film else 0, residual=residual, scale=scale,
             acc_scale=cw.acc_scale, passes=net.plane_passes, a2=a2, Cin2=cin2, w2=w2, stats=stats))
 
     def _fusable(self, H, W, *channels):
@@ -400,9 +411,9 @@ class _Plan:
     def _conv_fused(self, H, W, cin, cw: ConvWeight, out, cout_store, x0, C0, x1, C1, sc, sh, act, film=None,
                     residual=None, scale=1.0, shortcut_raw=None, stats=None):
         net, B = self.net, self.B
-        film_v, stride = None, 0
-        if film is not None:
-            film_v, stride = self.film[:, film:], self.film.shape[1]
+        film_v, has_film = None, film is not None
+        if has_film:
+            film_v = self.film[:, film:]
         kw = {}
         if shortcut_raw is not None:
             s0, S0, s1, S1 = shortcut_raw
@@ -411,13 +422,13 @@ class _Plan:
             w8 = cw.planes8()                          # built now, not inside a replayed / captured step
             self.steps.append(lambda: ops.conv2d_fused(
                 B, H, W, cin, w8, cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1,
-                sc=sc, sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=stride, residual=residual,
+                sc=sc, sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=self.film_stride if has_film else 0, residual=residual,
                 scale=scale, acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
                 a8_exp=cw.A8_EXP, **kw))
             return
         self.steps.append(lambda: ops.conv2d_fused(
             B, H, W, cin, cw.planes, cw.cout_pad, cw.ksize, out, cout_store, x0=x0, C0=C0, x1=x1, C1=C1, sc=sc,
-            sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=stride, residual=residual, scale=scale,
+            sh=sh, act=act, bias=cw.bias, film=film_v, film_stride=self.film_stride if has_film else 0, residual=residual, scale=scale,
             acc_scale=cw.acc_scale, stats=stats, passes=net.plane_passes, **kw))
 
     def _resblock(self, rb, x: Act, skip: Act = None, mode=0, want_stats=True) -> Act:
@@ -626,13 +637,20 @@ class _Plan:
         ar.release(h.t)
         self.out = pyramid
 
-    def run(self, x_planes, x_pyramid, t):
+    def run(self, x_planes, x_pyramid, t, uniform=False):
+        """``uniform``: every entry of ``t`` is the same time and the caller has already put its FiLM row into
+        ``self.film[0]`` (ScoreModelNCSNpp.prepare_times): the embedding MLP and the 49 Dense_0 projections — which
+        depend on ``t`` only — are not re-evaluated, and the convolutions read row 0 for every batch entry."""
         net, B = self.net, self.B
         self.x_planes, self.x_pyramid = x_planes, x_pyramid
         for chunk in self._stat_chunks:
             ops.zero(chunk)
-        ops.time_embedding(t, net.Wf, net.t_w1, net.t_b1, net.t_w2, net.t_b2, B, net.nf, self.temb_act)
-        ops.film(self.temb_act, net.dense_w, net.dense_b, B, net.temb_dim, net._film_rows, self.film)
+        if uniform:
+            self.film_stride = 0
+        else:
+            self.film_stride = net._film_rows
+            ops.time_embedding(t, net.Wf, net.t_w1, net.t_b1, net.t_w2, net.t_b2, B, net.nf, self.temb_act)
+            ops.film(self.temb_act, net.dense_w, net.dense_b, B, net.temb_dim, net._film_rows, self.film)
         for step in self.steps:
             step()
         return self.out

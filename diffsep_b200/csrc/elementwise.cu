@@ -409,13 +409,16 @@ fir_scalar_kernel(const float* __restrict__ x, int64_t total_out, int H, int W, 
 
 // ------------------------------------------------------------------------------ Combine
 // out[b,p,c] = h[b,p,c] + bias[c] + sum_k w[c,k] * pyr[b,p,k]
+// weights are staged transposed, s_w[k][c]: a warp reads 32 consecutive channel quads of one k with one
+// conflict-free LDS.128 per lane (the [c][k] order put the lanes' words 24 floats apart: 8-way bank conflicts,
+// 1.5 TB/s; profiles/membound_r02.md)
 __global__ void __launch_bounds__(256)
 combine_kernel(const float* __restrict__ pyr, int Cp, const float* __restrict__ w,
                const float* __restrict__ bias, const float* __restrict__ h, float* __restrict__ out,
                int64_t total_quads, int C) {
-    extern __shared__ float s_w[];   // [C * Cp] + [C]
+    extern __shared__ __align__(16) float s_w[];   // [Cp][C] + [C]
     float* s_b = s_w + C * Cp;
-    for (int i = threadIdx.x; i < C * Cp; i += blockDim.x) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < C * Cp; i += blockDim.x) s_w[(i % Cp) * C + i / Cp] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
     const int Q = C >> 2;
@@ -424,14 +427,14 @@ combine_kernel(const float* __restrict__ pyr, int Cp, const float* __restrict__ 
         const int q = static_cast<int>(e % Q);
         const int64_t pix = e / Q;
         const int c = q * 4;
-        float4 v = reinterpret_cast<const float4*>(h)[e];
-        float a[4] = {s_b[c], s_b[c + 1], s_b[c + 2], s_b[c + 3]};
+        float4 v = __ldg(reinterpret_cast<const float4*>(h) + e);
+        float4 a = *reinterpret_cast<const float4*>(s_b + c);
         for (int k = 0; k < Cp; ++k) {
-            const float pk = pyr[pix * Cp + k];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] += s_w[(c + u) * Cp + k] * pk;
+            const float pk = __ldg(pyr + pix * Cp + k);
+            const float4 wk = *reinterpret_cast<const float4*>(s_w + k * C + c);
+            a.x = fmaf(wk.x, pk, a.x); a.y = fmaf(wk.y, pk, a.y); a.z = fmaf(wk.z, pk, a.z); a.w = fmaf(wk.w, pk, a.w);
         }
-        v.x += a[0]; v.y += a[1]; v.z += a[2]; v.w += a[3];
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         reinterpret_cast<float4*>(out)[e] = v;
     }
 }

@@ -143,6 +143,12 @@ class DiffSepModel(torch.nn.Module):
     def cached_mixture(self, mix):
         return self.score_model.cached_mixture(mix)
 
+    def prepare_times(self, ts):
+        return self.score_model.prepare_times(ts)
+
+    def uniform_time(self, t):
+        return self.score_model.uniform_time(t)
+
     def get_pc_sampler(self, predictor_name, corrector_name, y, N=None, minibatch=None, schedule=None,
                        **kwargs):
         N = self.sde.N if N is None else N

@@ -97,6 +97,8 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self._bufs = {}
         self._mix_cache = None     # (data_ptr, B, T) of the mixture whose spectrogram is resident
         self._mix_cache_on = False
+        self._uniform_t = None     # host value of the time all batch entries share (set by the sampler), or None
+        self._film_cache = {}      # time -> its FiLM row [R] (device)
         self.use_cuda_graph = bool(int(os.environ.get("DSEP_CUDA_GRAPH", "1")))
         if state_dict is not None:
             self.load_state_dict(state_dict)
@@ -112,6 +114,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self.backbone = NCSNppB200(bb, nf=self.nf, ch_in=self.ch_in, ch_out=self.ch_out, device=self.dev,
                                    passes=self.passes)
         self._bufs = {}        # drops captured graphs that reference the old weights
+        self._film_cache = {}
         return self
 
     # -------------------------------------------------------------- buffers per (B, T)
@@ -155,6 +158,39 @@ class ScoreModelNCSNpp(torch.nn.Module):
         finally:
             self._mix_cache_on, self._mix_cache = prev
 
+    # -------------------------------------------------------------- time embedding hoisted out of the loop
+    def prepare_times(self, ts):
+        """The Fourier embedding, its two Linear layers and the 49 ``Dense_0`` FiLM projections depend on ``t`` only
+        (ncsnpp.py:324-343, layerspp.py:311-313) and the sampler's time grid is known up front: evaluate them for the
+        whole grid in one go instead of once per score evaluation."""
+        if self.backbone is None:
+            return
+        new = [float(t) for t in ts if float(t) not in self._film_cache]
+        if new:
+            rows = self.backbone.film_rows(new)
+            for i, t in enumerate(new):
+                self._film_cache[t] = rows[i]
+            while len(self._film_cache) > 4096:
+                self._film_cache.pop(next(iter(self._film_cache)))
+
+    @contextlib.contextmanager
+    def uniform_time(self, t):
+        """Within the context the caller guarantees that every entry of the ``time`` argument equals ``t`` (the PC
+        sampler: sdes/__init__.py:177-178), so the cached FiLM row of ``t`` serves the whole batch."""
+        prev = self._uniform_t
+        self._uniform_t = float(t)
+        try:
+            yield self
+        finally:
+            self._uniform_t = prev
+
+    def _film_row(self):
+        if self._uniform_t is None:
+            return None
+        if self._uniform_t not in self._film_cache:
+            self.prepare_times([self._uniform_t])
+        return self._film_cache[self._uniform_t]
+
     # -------------------------------------------------------------- forward
     @torch.no_grad()
     def forward(self, xt, time, mix):
@@ -176,7 +212,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         mix_key = (mix.data_ptr(), B, T)
         if self._mix_cache_on and self._mix_cache == mix_key:
             if self.use_cuda_graph:
-                return self._replay(xt, time, bf)
+                return self._replay(xt, time, bf, self._film_row())
         else:
             ops.stft_frames(mix, self.window, B, 1, T, Fr, bf["frames_mix"])
             ops.sgemm(bf["frames_mix"], LD, self.basis_fwd, LD, bf["dft_mix"], LD, B * Fr, LD, LD)
@@ -184,9 +220,9 @@ class ScoreModelNCSNpp(torch.nn.Module):
                           self.spec_abs_exponent,
                           bf["x_pyr"], bf["x_planes"])
             self._mix_cache = mix_key if self._mix_cache_on else None
-        return self._evaluate(xt, time, bf)
+        return self._evaluate(xt, time, bf, self._film_row())
 
-    def _evaluate(self, xt, time, bf):
+    def _evaluate(self, xt, time, bf, film_row=None):
         """Everything that depends on xt / t: the launch sequence one CUDA graph captures."""
         B, ns, T = xt.shape
         Fr, Wp = bf["Fr"], bf["Wp"]
@@ -195,7 +231,9 @@ class ScoreModelNCSNpp(torch.nn.Module):
         ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, bf["x_planes"].shape[-1], self.spec_factor,
                       self.spec_abs_exponent,
                       bf["x_pyr"], bf["x_planes"])
-        pyr = self.backbone(bf["x_planes"], bf["x_pyr"], time)
+        if film_row is not None:      # one row for the whole batch (uniform time); a no-op when replay already set it
+            self.backbone.plan(B, Wp).film[0].copy_(film_row)
+        pyr = self.backbone(bf["x_planes"], bf["x_pyr"], time, uniform=film_row is not None)
         ops.out_head(pyr, B, Wp, self.ch_in, ns, Fr, time, self.backbone.out_w, self.backbone.out_b,
                      self.spec_factor, self.spec_abs_exponent, bf["spec_out"])
         ops.sgemm(bf["spec_out"], LD, self.basis_inv, LD, bf["frames_out"], LD, B * ns * Fr, LD, LD)
@@ -203,26 +241,33 @@ class ScoreModelNCSNpp(torch.nn.Module):
         ops.istft_ola(bf["frames_out"], self.window, B, ns, Fr, T, out)
         return out
 
-    def _replay(self, xt, time, bf):
+    def _replay(self, xt, time, bf, film_row=None):
         """Inside a sampling run (mixture spectrogram resident) the ~300 launches of one evaluation
-        are replayed from a CUDA graph: static input buffers, one graph launch per evaluation."""
+        are replayed from a CUDA graph: static input buffers, one graph launch per evaluation.  With a uniform time
+        the graph holds no time-embedding / FiLM launches: it reads the row staged here (one small copy)."""
         from . import _lib
-        g = bf.get("graph")
+        key = "graph_u" if film_row is not None else "graph"
+        g = bf.get(key)
         if g is None:
             B, ns, T = xt.shape
             xs = torch.empty_like(xt)
             ts = torch.empty_like(time)
+            row = torch.empty_like(film_row) if film_row is not None else None
             xs.copy_(xt); ts.copy_(time)
-            self._evaluate(xs, ts, bf)                 # warm-up outside capture: plans, attributes
+            if row is not None:
+                row.copy_(film_row)
+            self._evaluate(xs, ts, bf, row)            # warm-up outside capture: plans, attributes
             torch.cuda.current_stream().synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.N_CALLS
             with torch.cuda.graph(graph):
-                out = self._evaluate(xs, ts, bf)
-            g = bf["graph"] = (graph, xs, ts, out, _lib.N_CALLS - n0)
-        graph, xs, ts, out, n_launches = g
+                out = self._evaluate(xs, ts, bf, row)
+            g = bf[key] = (graph, xs, ts, row, out, _lib.N_CALLS - n0)
+        graph, xs, ts, row, out, n_launches = g
         xs.copy_(xt)
         ts.copy_(time)
+        if row is not None:
+            row.copy_(film_row)
         graph.replay()
         _lib.N_CALLS += n_launches
         return out.clone()

@@ -51,13 +51,20 @@ def _make_sampler(predictor_name, corrector_name, sde, score_fn, y, true_mean, d
             # one host read of the grid: every batch entry shares t (sdes/__init__.py:177-178)
             ts = _timesteps(sde, eps, schedule, "cpu").tolist()
             vec_t = torch.empty(y.shape[0], device=y.device, dtype=torch.float32)
+            # the time embedding and the FiLM projections depend on t only and the grid is known: evaluate them for
+            # all N times now, and tell the score model which (shared) time each step is at
+            prepare = getattr(score_fn, "prepare_times", None)
+            uniform = getattr(score_fn, "uniform_time", None)
+            if prepare is not None:
+                prepare(ts[:sde.N])
             xt_mean = xt
             for i in range(sde.N):
                 vec_t.fill_(ts[i])
-                xt, xt_mean = corrector.update_fn(xt, vec_t, y)
-                if intermediate:
-                    im.append((xt, xt_mean))
-                xt, xt_mean = predictor.update_fn(xt, vec_t, y)
+                with (uniform(ts[i]) if uniform is not None else contextlib.nullcontext()):
+                    xt, xt_mean = corrector.update_fn(xt, vec_t, y)
+                    if intermediate:
+                        im.append((xt, xt_mean))
+                    xt, xt_mean = predictor.update_fn(xt, vec_t, y)
             x_result = xt_mean if denoise else xt
             ns = sde.N * (corrector.n_steps + 1)
             return (x_result, ns, im) if intermediate else (x_result, ns)

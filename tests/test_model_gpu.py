@@ -318,6 +318,24 @@ def test_score_model_e4m3_correction_mode_matches_reference_golden(golden):
     assert rel_l2(y.cpu(), g["y"]) < 1e-4
 
 
+def test_hoisted_time_embedding_equals_per_evaluation_one():
+    """prepare_times / uniform_time (the FiLM rows of the sampler's time grid evaluated once, row 0 serving the whole
+    batch) give the very bits of the per-evaluation time-embedding + Dense_0 kernels, with and without the CUDA graph."""
+    sm = _score_model(64)
+    xt, _, mix = (v.to(DEV) for v in cases.score_inputs(3, 2048, seed=4))
+    for tval in (1.0, 0.5166666507720947, 0.03):
+        t = torch.full((3,), tval, device=DEV)
+        ref = sm(xt, t, mix)
+        sm.prepare_times([tval])
+        with sm.uniform_time(tval):
+            got = sm(xt, t, mix)
+            with sm.cached_mixture(mix):
+                sm(xt, t, mix)                      # first call inside the context computes the mixture spectrogram
+                got_graph = sm(xt, t, mix)          # second one replays the graph
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref) and torch.equal(got_graph, ref), tval
+
+
 def test_score_model_argument_errors():
     sm = _score_model(64)
     xt, t, mix = (v.to(DEV) for v in cases.score_inputs(2, 1024))
