@@ -320,7 +320,7 @@ def test_score_model_e4m3_correction_mode_matches_reference_golden(golden):
 
 def test_hoisted_time_embedding_equals_per_evaluation_one():
     """prepare_times / uniform_time (the FiLM rows of the sampler's time grid evaluated once, row 0 serving the whole
-    batch) give the very bits of the per-evaluation time-embedding + Dense_0 kernels, with and without the CUDA graph."""
+    batch) reproduce the per-evaluation time-embedding + Dense_0 kernels, with and without the CUDA graph."""
     sm = _score_model(64)
     xt, _, mix = (v.to(DEV) for v in cases.score_inputs(3, 2048, seed=4))
     for tval in (1.0, 0.5166666507720947, 0.03):
@@ -333,7 +333,8 @@ def test_hoisted_time_embedding_equals_per_evaluation_one():
                 sm(xt, t, mix)                      # first call inside the context computes the mixture spectrogram
                 got_graph = sm(xt, t, mix)          # second one replays the graph
         torch.cuda.synchronize()
-        assert torch.equal(got, ref) and torch.equal(got_graph, ref), tval
+        # (not torch.equal: the GroupNorm sums are combined with fp64 atomics in an order that varies run to run)
+        assert rel_l2(got.cpu(), ref.cpu()) < 1e-6 and rel_l2(got_graph.cpu(), ref.cpu()) < 1e-6, tval
 
 
 def test_score_model_argument_errors():
