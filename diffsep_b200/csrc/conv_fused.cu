@@ -130,52 +130,58 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d
 template <bool E4M3>
 __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, bool silu, uint32_t dst_hi,
                                               uint32_t dst_2, float a8_lo) {
-    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
-    if (inside) {
-        float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        if (silu) {
+    // rows outside the image are computed like the others (on whatever the registers hold) and zeroed by selects at
+    // the end: one straight-line body per row instead of a branch around it
+    uint32_t hi[4], lo[4];
+    float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (silu) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float ex, rc;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(y[e]));
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(ex, kNegLog2e, kNegLog2e)));
-                y[e] *= rc;
-            }
-        }
-        if (E4M3) {
-            float l[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(y[2 * e + 1]), "f"(y[2 * e]));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
-                l[2 * e] = (y[2 * e] - b.x) * a8_lo;
-                l[2 * e + 1] = (y[2 * e + 1] - b.y) * a8_lo;
-            }
-            lo[0] = e4m3x4(l[0], l[1], l[2], l[3]);
-            lo[1] = e4m3x4(l[4], l[5], l[6], l[7]);
-            lo[2] = e4m3x2_from_f16x2(hi[0]) | (e4m3x2_from_f16x2(hi[1]) << 16);
-            lo[3] = e4m3x2_from_f16x2(hi[2]) | (e4m3x2_from_f16x2(hi[3]) << 16);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
+        for (int e = 0; e < 8; ++e) {
+            float ex, rc;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(y[e]));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(ex, kNegLog2e, kNegLog2e)));
+            y[e] *= rc;
         }
     }
+    if (E4M3) {
+        float l[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(y[2 * e + 1]), "f"(y[2 * e]));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
+            l[2 * e] = (y[2 * e] - b.x) * a8_lo;
+            l[2 * e + 1] = (y[2 * e + 1] - b.y) * a8_lo;
+        }
+        lo[0] = e4m3x4(l[0], l[1], l[2], l[3]);
+        lo[1] = e4m3x4(l[4], l[5], l[6], l[7]);
+        lo[2] = e4m3x2_from_f16x2(hi[0]) | (e4m3x2_from_f16x2(hi[1]) << 16);
+        lo[3] = e4m3x2_from_f16x2(hi[2]) | (e4m3x2_from_f16x2(hi[3]) << 16);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { hi[e] = inside ? hi[e] : 0u; lo[e] = inside ? lo[e] : 0u; }
     sts128(dst_hi, hi[0], hi[1], hi[2], hi[3]);
     sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
 }
 
-template <bool E4M3>
+// HALO3: the 10 x 18 patch of a 3x3 conv (6 rows per thread, 30 patch rows apart) — else 8 x 16 (4 rows, 32 apart):
+// compile-time geometry keeps the row / swizzle arithmetic in immediates.
+template <bool E4M3, bool HALO3>
 __device__ __forceinline__ void convert_rows(const float4 (&v)[6][2], const PatchPlan& cur, uint32_t slot_addr,
                                              uint32_t r0, uint32_t jchunk, float a8_lo) {
+    constexpr int kIter = HALO3 ? 6 : 4;
+    constexpr uint32_t kRows = HALO3 ? 30u : 32u;
+    if (cur.niter == 0u) return;                 // threads beyond the patch (r0 >= 30 in the halo geometry)
     const bool silu = cur.mode == 2;
+    const uint32_t base = slot_addr + r0 * 128u;
 #pragma unroll
-    for (int u = 0; u < 6; ++u) {
-        if (u < static_cast<int>(cur.niter)) {
-            const uint32_t r = r0 + static_cast<uint32_t>(u) * cur.krows;
-            const uint32_t off = r * 128u + ((jchunk ^ (r & 7u)) << 4);
-            convert_store<E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, slot_addr + off,
-                                slot_addr + kPatchPlane + off, a8_lo);
-        }
+    for (int u = 0; u < kIter; ++u) {
+        // (r0 + u * kRows) & 7 == (r0 + (u * kRows & 7)) & 7: only the low bits of r0 are runtime
+        const uint32_t sw = ((jchunk ^ ((r0 + ((u * kRows) & 7u)) & 7u)) << 4);
+        const uint32_t off = base + u * kRows * 128u + sw;
+        convert_store<E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, off, off + kPatchPlane, a8_lo);
     }
 }
 
@@ -432,8 +438,15 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         auto wait_slot = [&]() { mbar_wait(&aempty[as_], aph ^ 1u); };
         auto build = [&](const float4 (&v)[6][2], const PatchPlan& cur) {
             const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
-            if (FP8 && !cur.second) convert_rows<true>(v, cur, slot, r0, jchunk, a8_lo);
-            else convert_rows<false>(v, cur, slot, r0, jchunk, 0.f);
+            const bool halo3 = cur.krows == 30u;        // shortcut patches are never halo patches
+            if (FP8) {
+                if (cur.second) convert_rows<false, false>(v, cur, slot, r0, jchunk, 0.f);
+                else if (halo3) convert_rows<true, true>(v, cur, slot, r0, jchunk, a8_lo);
+                else convert_rows<true, false>(v, cur, slot, r0, jchunk, a8_lo);
+            } else {
+                if (halo3) convert_rows<false, true>(v, cur, slot, r0, jchunk, 0.f);
+                else convert_rows<false, false>(v, cur, slot, r0, jchunk, 0.f);
+            }
             // each builder warp publishes its own share (afull counts the builder warps)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
             __syncwarp();

@@ -261,6 +261,22 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
     const int c0 = chunk * 32;
     const bool xf = st != nullptr && a_hi != nullptr;
     const bool want_raw = r_hi != nullptr || y != nullptr;
+    // the patch loads go out first and stay in flight while 32 threads turn the GroupNorm sums into this chunk's
+    // scale / shift (both are one memory round trip; back to back they were ~2 of the ~8 us a block lives)
+    constexpr int NI = FT::IH * FT::IW * 8;
+    constexpr int PER = (NI + 255) / 256;
+    float4 raw[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * 256;
+        raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < NI) {
+            const int q = i & 7, pix = i >> 3;
+            const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                raw[k] = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + ih) * W + iw) * C + c0 + q * 4));
+        }
+    }
     if (threadIdx.x < 32) {
         float sc = 1.0f, sh = 0.0f;
         if (xf) {
@@ -281,19 +297,20 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
     }
     __syncthreads();
     // stage the patch: out-of-image pixels are zero AFTER the activation (the FIR pads its input)
-    for (int i = threadIdx.x; i < FT::IH * FT::IW * 8; i += blockDim.x) {
-        const int q = i & 7, pix = i >> 3;
-        const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
-        float4 raw = make_float4(0.f, 0.f, 0.f, 0.f), av = raw;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-            raw = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + ih) * W + iw) * C + c0 + q * 4));
-            if (a_hi != nullptr)
-                av = xf ? affine_act(raw, *reinterpret_cast<const float4*>(s_sc + q * 4),
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < NI) {
+            const int q = i & 7, pix = i >> 3;
+            const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_hi != nullptr && ih >= 0 && ih < H && iw >= 0 && iw < W)
+                av = xf ? affine_act(raw[k], *reinterpret_cast<const float4*>(s_sc + q * 4),
                                      *reinterpret_cast<const float4*>(s_sh + q * 4), true)
-                        : raw;
+                        : raw[k];
+            s_act[i] = av;
+            if (want_raw) s_raw[i] = raw[k];
         }
-        s_act[i] = av;
-        s_raw[i] = raw;
     }
     __syncthreads();
     const int Q = C >> 2;
