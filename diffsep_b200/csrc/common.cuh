@@ -73,18 +73,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Bounded wait: a broken pipeline traps (-> CUDA error on the host) within a few seconds instead of hanging the
 // box.  Each try suspends the warp in hardware for at most 20 us (a 10 ms hint once turned a lost wake-up into an
-// apparent hang of an experimental kernel variant); 2^18 tries ~ 5 s.
+// apparent hang of an experimental kernel variant); the try count bounds the total at ~5 s.
+template <uint32_t HINT_NS = 20000u>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
+    for (uint32_t spin = 0; spin < (5000000000ull / HINT_NS > 0xFFFFFFFFull ? 0xFFFFFFFFu : static_cast<uint32_t>(5000000000ull / HINT_NS)); ++spin) {
         asm volatile(
             "{\n\t.reg .pred P;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of polling
+            : "r"(addr), "r"(parity), "r"(HINT_NS)   // suspend-time hint (ns): sleep in hardware instead of polling
             : "memory");
         if (done) return;
     }

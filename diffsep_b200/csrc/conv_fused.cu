@@ -235,6 +235,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int total_patches = p.kblocks + p.kblocks2;
+    // TWO: the barriers a role waits on are completed from the other CTA (multicast commits of the leader's tensor
+    // core); such completions do not wake a suspended try_wait early (see mbar_wait_poll), so keep the hint short
+    auto role_wait = [](uint64_t* bar, uint32_t parity) {
+        if constexpr (TWO) mbar_wait<400u>(bar, parity);
+        else mbar_wait(bar, parity);
+    };
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -243,7 +249,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             int bs = 0;
             uint32_t bph = 0;
             auto load_weights = [&](const CUtensorMap* whi, const CUtensorMap* wlo, int kcol, int wrow) {
-                mbar_wait(&empty[bs], bph ^ 1u);
+                role_wait(&empty[bs], bph ^ 1u);
                 uint8_t* sb = stage_base + NA * Cfg::kAStage + bs * Cfg::kBStage;
                 const int wrow_h = wrow + static_cast<int>(rank) * (NT / 2);      // my half of the weight rows
                 if (p.debug & 2) {
@@ -435,7 +441,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         int as_ = 0;
         uint32_t aph = 0;
         const float negzero = -(p.acc_scale * 0.0f);
-        auto wait_slot = [&]() { mbar_wait(&aempty[as_], aph ^ 1u); };
+        auto wait_slot = [&]() { role_wait(&aempty[as_], aph ^ 1u); };
         auto build = [&](const float4 (&v)[6][2], const PatchPlan& cur) {
             const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
             const bool halo3 = cur.krows == 30u;        // shortcut patches are never halo patches
@@ -601,7 +607,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                 }
                 bz.x *= p.scale; bz.y *= p.scale; bz.z *= p.scale; bz.w *= p.scale;
                 if (!waited) {
-                    mbar_wait(&tfull[as], (it >> 1) & 1);
+                    role_wait(&tfull[as], (it >> 1) & 1);
                     tc_fence_after();
                     waited = true;
                 }
