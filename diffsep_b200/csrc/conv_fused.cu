@@ -40,7 +40,8 @@ struct FusedCfg {
     static constexpr int kBPlane = TWO ? kBBytes / 2 : kBBytes;   // this CTA's share of it
     static constexpr int kAStage = 2 * kPatchPlane;
     static constexpr int kBStage = 2 * kBPlane;
-    static constexpr int kStagingBytes = kFEpiWarps * 32 * 32 * 4;
+    static constexpr int kStatBytes = kFEpiWarps * (NT / 32) * 8 * 32;          // epilogue: running GroupNorm sums
+    static constexpr int kStagingBytes = kFEpiWarps * 32 * 32 * 4 + kStatBytes;
     static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes - kNA * kAStage;
     static constexpr int kBStagesMax = kAvail / kBStage;
     static constexpr int kBStages = kBStagesMax > 8 ? 8 : kBStagesMax;
@@ -490,34 +491,35 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         const int wq = warp & 3;               // TMEM lane quarter == warp_id % 4
         const float crel = FP8 ? p.corr_rel : 1.0f;
         constexpr int kChunks = NT / 32;       // 32-column chunks of the tile, all handled by this warp
-        float4 run1[kChunks], run2[kChunks];   // GroupNorm partial sums of this thread's 4 channels per chunk
+        // GroupNorm partial sums of the tile sequence of one (batch entry, channel tile): [chunk][channel quad q] x
+        // (sum, sum of squares) x 4 channels, kept in this warp's shared-memory scratch by lanes 0-7 (they used to be
+        // 32 registers per thread, which the residual double buffer below needs) and flushed with fp64 atomics when
+        // the batch entry / channel tile changes
+        const uint32_t sstat = smem_u32(reinterpret_cast<uint8_t*>(staging) + kFEpiWarps * 32 * 32 * 4 +
+                                        wq * (kChunks * 8 * 32)) + (lane & 7) * 32;
         int run_b = -1, run_n0 = -1;
-        auto flush_stats = [&]() {
-            if (p.stats == nullptr || run_b < 0) return;           // warp-uniform
+        auto zero_stats = [&]() {
+            if (lane < 8) {
 #pragma unroll
-            for (int c = 0; c < kChunks; ++c) {                     // rows of the 4 lane groups -> lanes 0..7
-#pragma unroll
-                for (int o = 8; o <= 16; o <<= 1) {
-                    run1[c].x += __shfl_xor_sync(0xffffffffu, run1[c].x, o);
-                    run1[c].y += __shfl_xor_sync(0xffffffffu, run1[c].y, o);
-                    run1[c].z += __shfl_xor_sync(0xffffffffu, run1[c].z, o);
-                    run1[c].w += __shfl_xor_sync(0xffffffffu, run1[c].w, o);
-                    run2[c].x += __shfl_xor_sync(0xffffffffu, run2[c].x, o);
-                    run2[c].y += __shfl_xor_sync(0xffffffffu, run2[c].y, o);
-                    run2[c].z += __shfl_xor_sync(0xffffffffu, run2[c].z, o);
-                    run2[c].w += __shfl_xor_sync(0xffffffffu, run2[c].w, o);
+                for (int c = 0; c < kChunks; ++c) {
+                    sts128(sstat + c * 256, 0u, 0u, 0u, 0u);
+                    sts128(sstat + c * 256 + 16, 0u, 0u, 0u, 0u);
                 }
             }
-            if (run_b >= p.B || (lane >> 3) != 0) return;
+        };
+        auto flush_stats = [&]() {
+            if (p.stats == nullptr || run_b < 0) return;           // warp-uniform
+            if (run_b >= p.B || lane >= 8) return;
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
-                const int n = run_n0 + c * 32 + (lane & 7) * 4;
+                const int n = run_n0 + c * 32 + lane * 4;
                 if (n < p.cout_store) {
+                    const float4 r1 = lds128(sstat + c * 256), r2 = lds128(sstat + c * 256 + 16);
                     double* st = p.stats + (static_cast<size_t>(run_b) * p.cout_store + n) * 2;
-                    atomicAdd(st + 0, (double)run1[c].x); atomicAdd(st + 1, (double)run2[c].x);
-                    atomicAdd(st + 2, (double)run1[c].y); atomicAdd(st + 3, (double)run2[c].y);
-                    atomicAdd(st + 4, (double)run1[c].z); atomicAdd(st + 5, (double)run2[c].z);
-                    atomicAdd(st + 6, (double)run1[c].w); atomicAdd(st + 7, (double)run2[c].w);
+                    atomicAdd(st + 0, (double)r1.x); atomicAdd(st + 1, (double)r2.x);
+                    atomicAdd(st + 2, (double)r1.y); atomicAdd(st + 3, (double)r2.y);
+                    atomicAdd(st + 4, (double)r1.z); atomicAdd(st + 5, (double)r2.z);
+                    atomicAdd(st + 6, (double)r1.w); atomicAdd(st + 7, (double)r2.w);
                 }
             }
         };
@@ -541,8 +543,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             if (p.stats != nullptr && (b0 != run_b || n0 != run_n0)) {
                 flush_stats();
                 run_b = b0; run_n0 = n0;
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) run1[c] = run2[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                zero_stats();
             }
             const bool whole = b0 < p.B && h0 + 16 <= p.H && w0 + 8 <= p.W && n0 + NT <= p.cout_store;
             if (p.residual != nullptr) {
@@ -584,17 +585,33 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                     if (b0 < p.B && hrow + (i >> 1) < p.H && wcol + 4 * (i & 1) < p.W) rowmask |= 1u << i;
             }
             bool waited = false;
+            // residual rows, double-buffered over the chunks: chunk c + 1's loads are issued while chunk c is
+            // processed (one chunk = ~1.5 k clk of distance; issued at their point of use they made the epilogue the
+            // kernel's critical path: 1.16 ms for MMAs + epilogue alone against 0.94 ms without a residual).  Same
+            // scoreboard trap as in the builders: the current buffer is "touched" (scaled in place) BEFORE the next
+            // burst is issued, with a warp barrier in between as a scheduling fence.
+            float4 res[2][8];
+            auto load_res = [&](int c, float4 (&r)[8]) {
+                const bool n_ok_c = whole || n0 + c * 32 + q * 4 < p.cout_store;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    r[i] = (n_ok_c && ((rowmask >> i) & 1u))
+                               ? ldg_stream(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            if (res0 != nullptr) load_res(0, res[0]);
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 const int n = n0 + c * 32 + q * 4;
                 const bool n_ok = whole || n < p.cout_store;
-                float4 res[8];
-                if (res0 != nullptr) {     // prefetch the residual while the accumulator is still being produced
+                if (res0 != nullptr) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        res[i] = (n_ok && ((rowmask >> i) & 1u))
-                                     ? ldg_stream(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 8; ++i) {
+                        res[c & 1][i].x *= p.scale; res[c & 1][i].y *= p.scale;
+                        res[c & 1][i].z *= p.scale; res[c & 1][i].w *= p.scale;
+                    }
+                    __syncwarp();
+                    if (c + 1 < kChunks) load_res(c + 1, res[(c + 1) & 1]);
                 }
                 float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n_ok) {
@@ -642,8 +659,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                         a.x = fmaf(a.x, as2, bz.x); a.y = fmaf(a.y, as2, bz.y);
                         a.z = fmaf(a.z, as2, bz.z); a.w = fmaf(a.w, as2, bz.w);
                         if (res0 != nullptr) {
-                            a.x = fmaf(res[i].x, p.scale, a.x); a.y = fmaf(res[i].y, p.scale, a.y);
-                            a.z = fmaf(res[i].z, p.scale, a.z); a.w = fmaf(res[i].w, p.scale, a.w);
+                            a.x += res[c & 1][i].x; a.y += res[c & 1][i].y;
+                            a.z += res[c & 1][i].z; a.w += res[c & 1][i].w;
                         }
                         if (store)
                             *reinterpret_cast<float4*>(out0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half) = a;
@@ -652,9 +669,21 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                         s2.z = fmaf(a.z, a.z, s2.z); s2.w = fmaf(a.w, a.w, s2.w);
                     }
                 }
-                if (p.stats != nullptr) {
-                    run1[c].x += s1.x; run1[c].y += s1.y; run1[c].z += s1.z; run1[c].w += s1.w;
-                    run2[c].x += s2.x; run2[c].y += s2.y; run2[c].z += s2.z; run2[c].w += s2.w;
+                if (p.stats != nullptr) {      // rows of the 4 lane groups -> lanes 0..7 -> the running sums
+#pragma unroll
+                    for (int o = 8; o <= 16; o <<= 1) {
+                        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+                        s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+                        s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+                    }
+                    if (lane < 8) {
+                        const float4 r1 = lds128(sstat + c * 256), r2 = lds128(sstat + c * 256 + 16);
+                        sts128(sstat + c * 256, __float_as_uint(r1.x + s1.x), __float_as_uint(r1.y + s1.y),
+                               __float_as_uint(r1.z + s1.z), __float_as_uint(r1.w + s1.w));
+                        sts128(sstat + c * 256 + 16, __float_as_uint(r2.x + s2.x), __float_as_uint(r2.y + s2.y),
+                               __float_as_uint(r2.z + s2.z), __float_as_uint(r2.w + s2.w));
+                    }
                 }
                 __syncwarp();
             }
