@@ -529,6 +529,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         const uint32_t ld_base = stg_s + rg * 128 + ((q ^ rg) << 4);         // row i at + i*512, ^ ((i&1) << 6)
         const float as2 = p.acc_scale * p.scale;
         const bool store = !(p.debug & 4);
+        float4 res[2][8];          // residual rows, double-buffered over the chunks (and across tiles, see below)
+        bool have0 = false;        // res[0] already holds chunk 0 of the tile about to be processed
         int it = 0;
         for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
             const int as = it & 1;
@@ -546,16 +548,18 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                 zero_stats();
             }
             const bool whole = b0 < p.B && h0 + 16 <= p.H && w0 + 8 <= p.W && n0 + NT <= p.cout_store;
+            const float* next_res0 = nullptr;      // chunk 0 of the NEXT tile, if that tile lies whole inside the map
             if (p.residual != nullptr) {
-                // pull the NEXT tile's residual rows into L2 now (no registers, a whole tile period of lead time): the
-                // 4 epilogue warps cannot keep a tile's worth of residual loads in flight, and each chunk's loads
-                // coming from HBM cost the level-0 conv 0.2 ms (1.38 vs 1.19 ms)
+                // pull the NEXT tile's residual rows into L2 now (no registers, a whole tile period of lead time)
                 const int nitem = item + num_clusters;
                 if (nitem < p.total_items) {
                     int r2 = 2 * (nitem / p.tiles_n) + static_cast<int>(rank);
                     const int wt2 = r2 % p.tiles_w; r2 /= p.tiles_w;
                     const int ht2 = r2 % p.tiles_h; r2 /= p.tiles_h;
                     const int hr2 = (ht2 << 4) + wq * 4, wc2 = (wt2 << 3) + rg, n02 = (nitem % p.tiles_n) * NT;
+                    if (r2 < p.B && (ht2 << 4) + 16 <= p.H && (wt2 << 3) + 8 <= p.W && n02 + NT <= p.cout_store)
+                        next_res0 = p.residual + ((static_cast<size_t>(r2) * p.H + hr2) * p.W + wc2) * p.cout_store
+                                    + n02 + q * 4;
                     if (r2 < p.B && q < kChunks) {        // lane q of each row group takes the row's q-th 128-byte line
                         const float* base = p.residual + ((static_cast<size_t>(r2) * p.H + hr2) * p.W + wc2) * p.cout_store
                                             + n02 + q * 32;
@@ -585,12 +589,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                     if (b0 < p.B && hrow + (i >> 1) < p.H && wcol + 4 * (i & 1) < p.W) rowmask |= 1u << i;
             }
             bool waited = false;
-            // residual rows, double-buffered over the chunks: chunk c + 1's loads are issued while chunk c is
+            // residual rows: chunk c + 1's loads are issued while chunk c is
             // processed (one chunk = ~1.5 k clk of distance; issued at their point of use they made the epilogue the
             // kernel's critical path: 1.16 ms for MMAs + epilogue alone against 0.94 ms without a residual).  Same
             // scoreboard trap as in the builders: the current buffer is "touched" (scaled in place) BEFORE the next
             // burst is issued, with a warp barrier in between as a scheduling fence.
-            float4 res[2][8];
             auto load_res = [&](int c, float4 (&r)[8]) {
                 const bool n_ok_c = whole || n0 + c * 32 + q * 4 < p.cout_store;
 #pragma unroll
@@ -599,7 +602,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                                ? ldg_stream(res0 + c * 32 + (i >> 1) * d_row + (i & 1) * d_half)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            if (res0 != nullptr) load_res(0, res[0]);
+            if (res0 != nullptr && !have0) load_res(0, res[0]);
+            have0 = false;
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 const int n = n0 + c * 32 + q * 4;
@@ -611,7 +615,16 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                         res[c & 1][i].z *= p.scale; res[c & 1][i].w *= p.scale;
                     }
                     __syncwarp();
-                    if (c + 1 < kChunks) load_res(c + 1, res[(c + 1) & 1]);
+                    if (c + 1 < kChunks) {
+                        load_res(c + 1, res[(c + 1) & 1]);
+                    } else if (next_res0 != nullptr && (kChunks & 1) == 0) {
+                        // last chunk: res[0] is free — chunk 0 of the next tile goes out now, so that no tile starts
+                        // with an exposed memory round trip
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            res[0][i] = ldg_stream(next_res0 + (i >> 1) * d_row + (i & 1) * d_half);
+                        have0 = true;
+                    }
                 }
                 float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n_ok) {
