@@ -49,13 +49,9 @@ def built_hash():
     """the source hash embedded in the existing libdsep.so (None: no library / an older build without one)"""
     if not LIB.exists():
         return None
-    import ctypes
-    try:
-        lib = ctypes.CDLL(str(LIB))
-        lib.dsep_source_hash.restype = ctypes.c_char_p
-        return lib.dsep_source_hash().decode()
-    except (OSError, AttributeError):
-        return None
+    import re
+    m = re.search(rb"dsep-source-hash=([0-9a-f]{16}|unknown)\0", LIB.read_bytes())
+    return m.group(1).decode() if m else None
 
 
 def needs_build() -> bool:

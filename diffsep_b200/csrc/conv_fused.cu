@@ -41,7 +41,8 @@ struct FusedCfg {
     static constexpr int kAStage = 2 * kPatchPlane;
     static constexpr int kBStage = 2 * kBPlane;
     static constexpr int kStatBytes = kFEpiWarps * (NT / 32) * 8 * 32;          // epilogue: running GroupNorm sums
-    static constexpr int kStagingBytes = kFEpiWarps * 32 * 32 * 4 + kStatBytes;
+    static constexpr int kBiasBytes = kFEpiWarps * (NT / 32) * 32 * 16;         // epilogue: (bias + FiLM) * scale per lane
+    static constexpr int kStagingBytes = kFEpiWarps * 32 * 32 * 4 + kStatBytes + kBiasBytes;
     static constexpr int kAvail = 232448 - 1024 - 512 - kStagingBytes - kNA * kAStage;
     static constexpr int kBStagesMax = kAvail / kBStage;
     static constexpr int kBStages = kBStagesMax > 8 ? 8 : kBStagesMax;
@@ -497,6 +498,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         // the batch entry / channel tile changes
         const uint32_t sstat = smem_u32(reinterpret_cast<uint8_t*>(staging) + kFEpiWarps * 32 * 32 * 4 +
                                         wq * (kChunks * 8 * 32)) + (lane & 7) * 32;
+        // (bias + FiLM) * scale of this lane's 4 channels per chunk: loaded in ONE burst at the top of a tile into a
+        // lane-private shared-memory slot (per chunk it was a global load with its latency exposed four times a tile)
+        const uint32_t sbias = smem_u32(reinterpret_cast<uint8_t*>(staging) + kFEpiWarps * 32 * 32 * 4 + Cfg::kStatBytes +
+                                        wq * (kChunks * 32 * 16)) + lane * 16;
         int run_b = -1, run_n0 = -1;
         auto zero_stats = [&]() {
             if (lane < 8) {
@@ -604,6 +609,27 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
             };
             if (res0 != nullptr && !have0) load_res(0, res[0]);
             have0 = false;
+            {
+                float4 bz_all[kChunks];
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
+                    const int n = n0 + c * 32 + q * 4;
+                    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (whole || n < p.cout_store) {
+                        if (p.bias != nullptr) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                        if (p.film != nullptr && b0 < p.B) {
+                            const float4 f = __ldg(reinterpret_cast<const float4*>(
+                                p.film + static_cast<size_t>(b0) * p.film_stride + n));
+                            bz.x += f.x; bz.y += f.y; bz.z += f.z; bz.w += f.w;
+                        }
+                    }
+                    bz_all[c] = bz;
+                }
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c)
+                    sts128(sbias + c * 512, __float_as_uint(bz_all[c].x * p.scale), __float_as_uint(bz_all[c].y * p.scale),
+                           __float_as_uint(bz_all[c].z * p.scale), __float_as_uint(bz_all[c].w * p.scale));
+            }
 #pragma unroll
             for (int c = 0; c < kChunks; ++c) {
                 const int n = n0 + c * 32 + q * 4;
@@ -626,16 +652,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
                         have0 = true;
                     }
                 }
-                float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n_ok) {
-                    if (p.bias != nullptr) bz = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                    if (p.film != nullptr && b0 < p.B) {
-                        const float4 f = __ldg(reinterpret_cast<const float4*>(
-                            p.film + static_cast<size_t>(b0) * p.film_stride + n));
-                        bz.x += f.x; bz.y += f.y; bz.z += f.z; bz.w += f.w;
-                    }
-                }
-                bz.x *= p.scale; bz.y *= p.scale; bz.z *= p.scale; bz.w *= p.scale;
+                const float4 bz = lds128(sbias + c * 512);
                 if (!waited) {
                     role_wait(&tfull[as], (it >> 1) & 1);
                     tc_fence_after();

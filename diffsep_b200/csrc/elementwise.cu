@@ -488,7 +488,10 @@ extern "C" int dsep_abi_version(void) { return DSEP_ABI_VERSION; }
 #ifndef DSEP_SOURCE_HASH
 #define DSEP_SOURCE_HASH "unknown"
 #endif
-extern "C" const char* dsep_source_hash(void) { return DSEP_SOURCE_HASH; }
+// "dsep-source-hash=<hash>" as one literal: build.py finds the tag by scanning the file, without dlopen()ing a
+// possibly stale library into the process that is about to replace it
+static const char kSourceHashTag[] = "dsep-source-hash=" DSEP_SOURCE_HASH;
+extern "C" const char* dsep_source_hash(void) { return kSourceHashTag + 17; }
 extern "C" int dsep_device_ok(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
