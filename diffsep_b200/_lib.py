@@ -70,7 +70,7 @@ PROTOTYPES = {
     "dsep_randn": [_p, _i64, _u64, _u64, _p],
 }
 OTHER_SYMBOLS = ("dsep_last_error", "dsep_abi_version", "dsep_device_ok", "dsep_conv_kblock", "dsep_has_fp8_corr",
-                 "dsep_source_hash")
+                 "dsep_source_hash", "dsep_conv_wide_launches")
 
 _lib = None
 
@@ -100,6 +100,7 @@ def load():
     lib.dsep_device_ok.restype = C.c_int
     lib.dsep_conv_kblock.restype = C.c_int
     lib.dsep_has_fp8_corr.restype = C.c_int
+    lib.dsep_conv_wide_launches.restype = C.c_int
     lib.dsep_source_hash.restype = C.c_char_p
     if lib.dsep_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libdsep.so ABI {lib.dsep_abi_version()} != expected {ABI_VERSION}; rebuild")

@@ -48,8 +48,9 @@ def gn_groups(c):
 
 
 def _prescale_exp(amax):
-    """power of two k with amax * 2^k in [1024, 2048): both fp16 planes of a weight stay normal."""
-    return 0 if amax == 0.0 else 10 - math.floor(math.log2(amax))
+    """power of two k with amax * 2^k in [2^14, 2^15): both fp16 planes of a weight stay normal, and the e4m3 planes
+    of the 2-unit mode (W_hi * 2^-11 < 16, W_lo <= 16) keep 13 binades below the largest weight."""
+    return 0 if amax == 0.0 else 14 - math.floor(math.log2(amax))
 
 
 class ConvWeight:
@@ -100,7 +101,9 @@ class ConvWeight:
     # ---- passes = 2: e4m3 correction plane
     A8_EXP = 0            # activations enter the e4m3 planes as A_hi (saturating above 448) and A_lo * 2^11; with no
                           # prescale the builder converts A_hi8 straight from the packed fp16 pairs
-    W8_EXP = -3           # fp16 weight planes hold |W * 2^k| < 2048: W_hi * 2^-3 < 256 and W_lo * 2^8 <= 128 fit e4m3
+    W8_EXP = -11          # W_hi8 = e4m3(W_hi * 2^-11), W_lo8 = e4m3(W_lo): with A_lo8 = e4m3(A_lo * 2^11) and A_hi8 =
+                          # e4m3(A_hi) both correction products come out at the scale of the fp16 product, so all three
+                          # accumulate into ONE TMEM accumulator (corr_rel == 1; conv_wide.cu relies on it)
 
     def planes8(self) -> Split:
         """(hi = the fp16 hi plane, lo = the e4m3 plane [taps, Cout_pad, 2 * Cin_pad] bytes viewed as fp16): per 8

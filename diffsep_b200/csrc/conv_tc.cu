@@ -1083,6 +1083,8 @@ static int ilog2(int v) {
 
 extern "C" int dsep_conv_kblock(void) { return dsep::kBK; }
 
+static int g_wide_launches = 0;
+
 // corr_rel / a8_exp: only for passes = 2 (dsep_conv2d_fused8); dsep_conv2d_fused passes (1, 0)
 static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, dsep_stream_t stream) {
     using namespace dsep;
@@ -1143,8 +1145,14 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
                      "conv2d_fused: shortcut operand channels (%d + %d) must be multiples of 64 adding up to Cin2=%d",
                      g->S0, g->S1, Cin2);
     }
-    if (halo) { tw = 8; th = 16; }
-    const int tb = 128 / (tw * th);
+    // wide form (conv_wide.cu): 8 x 32 pixel tiles on the MMA's N side, one accumulator for all three products
+    static const int wide_env = getenv("DSEP_CONV_WIDE") ? atoi(getenv("DSEP_CONV_WIDE")) : 1;
+    static const int v2_env = getenv("DSEP_CONV_V2") ? atoi(getenv("DSEP_CONV_V2")) : 1;
+    static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
+    const bool wide = halo && main_fused && NT == 128 && passes == 2 && a8_exp == 0 && corr_rel == 1.0f &&
+                      H % 32 == 0 && W % 8 == 0 && wide_env != 0 && v2_env != 0 && !two_env;
+    if (halo) { tw = 8; th = wide ? 32 : 16; }
+    const int tb = wide ? 1 : 128 / (tw * th);
     DSEP_REQUIRE(g->stats == nullptr || (Cout_pad != 16 && tb == 1),
                  "conv2d_tc: fused statistics need Cout >= 64 and 128-pixel tiles inside one batch entry "
                  "(got %dx%d, tile %dx%dx%d)", H, W, th, tw, tb);
@@ -1221,10 +1229,13 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
         }
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static const int two_env = getenv("DSEP_CONV_2CTA") ? atoi(getenv("DSEP_CONV_2CTA")) : 0;
-    // Cout >= 64 with the operand built in-kernel: the role-split kernel of conv_fused.cu (DSEP_CONV_V2=0: the
-    // previous one-worker-role halo kernel below, kept for A/B timing)
-    static const int v2_env = getenv("DSEP_CONV_V2") ? atoi(getenv("DSEP_CONV_V2")) : 1;
+    // Cout >= 64 with the operand built in-kernel: the role-split kernels of conv_wide.cu / conv_fused.cu
+    // (DSEP_CONV_WIDE=0: 128-pixel tiles only; DSEP_CONV_V2=0: the previous one-worker-role halo kernel below, kept
+    // for A/B timing)
+    if (wide) {
+        ++g_wide_launches;
+        return launch_conv_wide(m, p, s);
+    }
     if (halo && main_fused && NT >= 64 && passes != 1 && v2_env != 0 && !two_env && (passes != 2 || a8_exp == 0))
         return launch_conv_fused(m, p, NT, s);
     if (halo && NT == 16) return launch_conv<16, true>(m, p, s);
@@ -1249,6 +1260,7 @@ extern "C" int dsep_conv2d_fused(const dsep_conv_args* g, dsep_stream_t stream) 
 }
 
 extern "C" int dsep_has_fp8_corr(void) { return DSEP_FP8_CORR; }
+extern "C" int dsep_conv_wide_launches(void) { return g_wide_launches; }
 
 extern "C" int dsep_conv2d_fused8(const dsep_conv_args* g, float corr_rel, int a8_exp, dsep_stream_t stream) {
 #if DSEP_FP8_CORR

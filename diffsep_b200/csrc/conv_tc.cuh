@@ -129,5 +129,7 @@ struct ConvMaps {
 int conv_num_sms();
 // conv_fused.cu: launches conv_fused_kernel<NT, FP8> (NT = 64 / 128; p.passes = 2 or 3; p.fx0 != nullptr)
 int launch_conv_fused(const ConvMaps& m, const ConvParams& p, int NT, cudaStream_t stream);
+// conv_wide.cu: conv_wide_kernel (Cout tile 128, passes = 2 with corr_rel == 1, 8 x 32 pixel tiles: H % 32 == 0, W % 8 == 0)
+int launch_conv_wide(const ConvMaps& m, const ConvParams& p, cudaStream_t stream);
 
 }  // namespace dsep

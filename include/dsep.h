@@ -115,6 +115,10 @@ int dsep_conv2d_fused(const dsep_conv_args* args, dsep_stream_t stream);
  * Needs Cout >= 64 and a map of at least 16 x 8 (the halo kernel). */
 int dsep_conv2d_fused8(const dsep_conv_args* args, float corr_rel, int a8_exp, dsep_stream_t stream);
 int dsep_has_fp8_corr(void);
+/* How many of the dsep_conv2d_fused8 calls of this process took the wide-tile kernel (conv_wide.cu: with corr_rel == 1,
+ * x0 given, Cout_pad % 128 == 0, H % 32 == 0 and W % 8 == 0 the same convolution runs on 8 x 32 pixel tiles with the
+ * pixels on the tensor core's N side).  A counter for tests and profiles, not part of the data path. */
+int dsep_conv_wide_launches(void);
 /* Per-(batch entry, channel) GroupNorm scale / shift from per-channel sums of a (concatenated) input:
  * sc = gamma * rstd[group], sh = beta - mean[group] * sc, so that GN(x) = x * sc + sh.  sc, sh: [B, C0+C1]. */
 int dsep_gn_tables(const double* st0, int C0, const double* st1, int C1, int B, int P, int groups,

@@ -1,6 +1,7 @@
 """GPU parity of every libdsep kernel (through the C-ABI) against the CPU oracle / plain fp32-fp64
 torch restatements of the same op on the same seeded inputs.  Tolerances are written per test."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -310,6 +311,79 @@ def test_conv2d_fused8_e4m3_corrections(shape):
     assert rel_l2(nchw(out), ref) < 3e-5
     got = nchw(out).double()
     assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
+
+
+# (B, H, W, C0, C1, Cout, ksize, shortcut, mode): maps made of whole 8 x 32 tiles -> conv_wide_kernel
+@pytest.mark.parametrize("shape", [(2, 32, 24, 128, 0, 128, 3, 0, "film"), (3, 64, 16, 64, 64, 256, 3, 1, "plain"),
+                                   (1, 96, 40, 128, 128, 128, 3, 1, "residual"), (3, 32, 8, 128, 0, 384, 1, 0, "plain"),
+                                   (1, 128, 64, 192, 64, 128, 3, 0, "residual")])
+def test_conv2d_wide_tiles(shape):
+    """passes = 2 on maps of whole 8 x 32 pixel tiles with Cout % 128 == 0: the wide-tile kernel (conv_wide.cu: output
+    channels on the tensor core's M side, 256 pixels on its N side, ONE accumulator for hi*hi and both e4m3
+    corrections) — 3x3 with channel concat, fused fp16 1x1 shortcut on the raw concat, FiLM / residual / scale, the
+    next GroupNorm's statistics, an odd number of tiles (the idle half of the last CTA pair), two channel tiles, and
+    the 1x1 form (GroupNorm without SiLU + stacked q/k/v) — vs float64."""
+    ops = _ops()
+    from diffsep_b200 import _lib
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, C0, C1, Cout, k, with_short, mode = shape
+    Ct = C0 + C1
+    g = cases.gen(sum(shape[:7]) + 5)
+    x0 = torch.randn(B, C0, H, W, generator=g) * 1.3 + 0.2
+    x1 = torch.randn(B, C1, H, W, generator=g) * 0.7 - 0.1 if C1 else None
+    xcat = torch.cat([x0, x1], 1) if C1 else x0
+    gamma = 1 + 0.1 * torch.randn(Ct, generator=g)
+    beta = 0.1 * torch.randn(Ct, generator=g)
+    groups = min(Ct // 4, 32)
+    w = torch.randn(Cout, Ct, k, k, generator=g) / math.sqrt(Ct * k * k)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    act = 1 if k == 3 else 0
+    a_ref = F.group_norm(xcat.double(), groups, gamma.double(), beta.double(), eps=1e-6)
+    if act:
+        a_ref = a_ref * torch.sigmoid(a_ref)
+    ref = F.conv2d(a_ref, w.double(), b1.double(), padding=k // 2)
+    shortcut = None
+    if with_short:
+        w2 = torch.randn(Cout, Ct, 1, 1, generator=g) / math.sqrt(Ct)
+        b2 = torch.randn(Cout, generator=g) * 0.1
+        shortcut = (w2, b2)
+        ref = ref + F.conv2d(xcat.double(), w2.double(), b2.double())
+    cw = ConvWeight(w, b1, DEV, shortcut=shortcut)
+    assert cw.corr_rel == 1.0
+    d0, d1 = cl(x0), (cl(x1) if C1 else None)
+    st0 = torch.empty(B, C0, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, C0, B, H * W, st0)
+    st1 = None
+    if C1:
+        st1 = torch.empty(B, C1, 2, dtype=torch.float64, device=DEV)
+        ops.channel_stats(d1, C1, B, H * W, st1)
+    sc = torch.empty(B, Ct, device=DEV)
+    sh = torch.empty(B, Ct, device=DEV)
+    ops.gn_tables(st0, C0, st1, C1, B, H * W, groups, gamma.to(DEV), beta.to(DEV), 1e-6, sc, sh)
+    kw = dict(s0=d0, S0=C0, s1=d1, S1=C1, Cin2=Ct, w2=cw.planes2) if with_short else {}
+    scale = 1.0
+    if mode == "film":
+        film = torch.randn(B, Cout + 8, generator=g) * 0.3
+        ref = ref + film[:, :Cout].double()[:, :, None, None]
+        kw.update(film=film.to(DEV), film_stride=Cout + 8)
+    elif mode == "residual":
+        res = torch.randn(B, Cout, H, W, generator=g)
+        scale = 1 / math.sqrt(2.0)
+        ref = (ref + res.double()) * scale
+        kw.update(residual=cl(res), scale=scale)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    stats = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    n_wide = _lib.load().dsep_conv_wide_launches()
+    ops.conv2d_fused(B, H, W, Ct, cw.planes8(), cw.cout_pad, k, out, Cout, x0=d0, C0=C0, x1=d1, C1=C1, sc=sc, sh=sh,
+                     act=act, bias=cw.bias, acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
+                     a8_exp=cw.A8_EXP, **kw)
+    torch.cuda.synchronize()
+    if os.environ.get("DSEP_CONV_WIDE", "1") != "0":
+        assert _lib.load().dsep_conv_wide_launches() == n_wide + 1, "the wide-tile kernel did not take this shape"
+    assert rel_l2(nchw(out), ref) < 3e-5
+    got = nchw(out).double()
+    assert rel_l2(stats[..., 0].cpu(), got.sum(dim=(2, 3))) < 1e-6
+    assert rel_l2(stats[..., 1].cpu(), (got * got).sum(dim=(2, 3))) < 1e-6
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 12, 128, 128, 1), (1, 64, 32, 128, 256, 2), (1, 32, 16, 256, 128, 2)])
