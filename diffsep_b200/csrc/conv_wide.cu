@@ -213,7 +213,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         }
     } else if (warp < 4 + kWBuilderWarps) {
         // ---------------------------------------------------------------------- patch builders
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const int wtid = static_cast<int>(threadIdx.x) - 128;
         const uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
         const uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
@@ -222,14 +222,45 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         const float a8_lo = p.a8_lo;
 
         // generator of this CTA's half-patch sequence: tiles in schedule order, per tile the shortcut K-blocks then
-        // the main ones (the order the MMA issuer consumes them in), per patch the upper then the lower half
+        // the main ones (the order the MMA issuer consumes them in), per patch the upper then the lower half.
+        // Everything that depends only on (thread, tile) is computed when the tile changes (retile): the pixel index
+        // of the thread's first row and the in-image masks of both halves for both patch forms; a plan then costs a
+        // source select and one 64-bit multiply-add (it used to redo the index arithmetic and the six-row mask loop
+        // per half patch: 11 % of the kernel's instructions, profiles/conv_regions_r2b.md).
         int g_item = cluster_id, g_pi = 0, g_half = 0;
-        int g_w0 = 0, g_h0 = 0, g_b0 = 0;
         bool g_valid = g_item < p.total_items;
-        if (g_valid) locate(g_item, g_w0, g_h0, g_b0);
-        // geometry of this thread inside a half patch (both forms), fixed for the whole launch
-        const int py3 = static_cast<int>(r0) / kPatchW, px3 = static_cast<int>(r0) - py3 * kPatchW;
-        const int py1 = static_cast<int>(r0) >> 3, px1 = static_cast<int>(r0) & 7;
+        const int py3 = static_cast<int>(r0) / kPatchW, px3 = static_cast<int>(r0) - py3 * kPatchW;   // 3x3 halo form
+        const int py1 = static_cast<int>(r0) >> 3, px1 = static_cast<int>(r0) & 7;                     // 1x1 form
+        const bool act3 = r0 < 30u;
+        uint32_t sm3 = 0;                       // bits 6h + u: row u of half h exists (the patch has 34 rows of 10)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+                if (act3 && 18 * h + py3 + 3 * u < 34) sm3 |= 1u << (6 * h + u);
+        int pix3 = 0, pix1 = 0, g_bs = 0;       // pixel index of row u = 0 of half 0 (3x3 / 1x1 form); batch entry
+        uint32_t inb3 = 0, inb1 = 0;            // in-image masks: bits 6h + u (3x3), 4 bits (1x1: whole tiles)
+        auto retile = [&]() {
+            int w0, h0, b0;
+            locate(g_item, w0, h0, b0);
+            const bool b_ok = b0 < p.B;
+            g_bs = b_ok ? b0 : 0;
+            const int w3 = w0 - 1 + px3;
+            const bool col3 = b_ok && w3 >= 0 && w3 < p.W;
+            uint32_t m = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int u = 0; u < 6; ++u) {
+                    const int hh = h0 - 1 + 18 * h + py3 + 3 * u;
+                    if (col3 && hh >= 0 && hh < p.H) m |= 1u << (6 * h + u);
+                }
+            inb3 = skip ? 0u : (m & sm3);
+            inb1 = (b_ok && !skip) ? 0xFu : 0u;
+            pix3 = (g_bs * p.H + h0 - 1 + py3) * p.W + w3;
+            pix1 = (g_bs * p.H + h0 + py1) * p.W + w0 + px1;
+        };
+        if (g_valid) retile();
         struct Half { PatchPlan d; uint32_t off; uint32_t rbias; };     // + where the half lies in its plane
         auto next_plan = [&](Half& hp) {            // plan of (g_item, g_pi, g_half), then advance
             PatchPlan& d = hp.d;
@@ -242,27 +273,14 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
             const int C0 = second ? p.gC0 : p.fC0, C1 = second ? p.gC1 : p.fC1;
             const float* src; int cs, cl;
             if (c < C0) { src = x0; cs = C0; cl = c; } else { src = x1; cs = C1; cl = c - C0; }
-            const int kdy = halo3 ? 3 : 4;
             d.krows = halo3 ? 30u : 32u;
-            d.niter = r0 < d.krows ? (halo3 ? 6u : 4u) : 0u;
-            // first patch row of this half: image row h0 - 1 + 18 * half (3x3) / h0 + 16 * half (1x1)
-            const int pyh = (halo3 ? 18 : 16) * g_half + (halo3 ? py3 : py1);      // this thread's row u = 0
-            const int w = g_w0 + (halo3 ? px3 - 1 : px1);
-            const int h0 = g_h0 + pyh - (halo3 ? 1 : 0);
-            const bool col_ok = d.niter != 0u && g_b0 < p.B && w >= 0 && w < p.W;
-            d.src = src + (((static_cast<long long>(g_b0) * p.H + h0) * p.W + w) * cs + cl);
-            d.step = static_cast<uint32_t>(kdy * p.W * cs);
-            uint32_t inb = 0, smask = 0;
-#pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                const int h = h0 + kdy * u;
-                const bool exists = u < static_cast<int>(d.niter) && (!halo3 || pyh + 3 * u < 34);
-                if (exists) smask |= 1u << u;
-                if (exists && col_ok && h >= 0 && h < p.H) inb |= 1u << u;
-            }
-            d.inb = skip ? 0u : inb;
-            d.smask = smask;
-            d.so = static_cast<uint32_t>((g_b0 < p.B ? g_b0 : 0) * (C0 + C1) + c);
+            d.niter = halo3 ? (act3 ? 6u : 0u) : 4u;
+            const int pix = halo3 ? pix3 + g_half * 18 * p.W : pix1 + g_half * 16 * p.W;
+            d.src = src + (static_cast<long long>(pix) * cs + cl);
+            d.step = static_cast<uint32_t>((halo3 ? 3 : 4) * p.W * cs);
+            d.inb = halo3 ? (inb3 >> (6 * g_half)) & 63u : inb1;
+            d.smask = halo3 ? (sm3 >> (6 * g_half)) & 63u : 0xFu;
+            d.so = static_cast<uint32_t>(g_bs * (C0 + C1) + c);
             d.second = second;
             d.mode = second ? 0 : (p.fact ? 2 : 1);
             hp.off = static_cast<uint32_t>(g_half) * (halo3 ? Cfg::kHalfRows3 : Cfg::kHalfRows1) * 128u;
@@ -273,7 +291,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
                     g_pi = 0;
                     g_item += num_clusters;
                     g_valid = g_item < p.total_items;
-                    if (g_valid) locate(g_item, g_w0, g_h0, g_b0);
+                    if (g_valid) retile();
                 }
             }
         };
@@ -325,7 +343,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         }
     } else {
         // ---------------------------------------------------------------------- epilogue (4 warps)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         const int wq = warp & 3;               // TMEM lane quarter == warp_id % 4: channels n0 + 32 wq + lane
         const float as2 = p.acc_scale * p.scale;
         const bool store = !(p.debug & 4);

@@ -27,7 +27,24 @@ def find(marker):
     raise SystemExit(f"marker not found: {marker}")
 
 
-marks = sorted([
+WIDE = "conv_wide" in fname
+if WIDE:
+    marks = sorted([
+        ("setup", find("conv_wide_kernel(const __grid_constant__")),
+        ("tma", find("TMA producer: weight stages")),
+        ("mma", find("--- MMA issuer")),
+        ("builder:plan", find("--- patch builders")),
+        ("builder:loop", find("float4 vx[6][2], vy[6][2];")),
+        ("epi:setup", find("--- epilogue (4 warps)")),
+        ("epi:tile-head", find("const int as = it & 1;")),
+        ("epi:residual", find("touch the current buffer BEFORE")),
+        ("epi:tmem", find("uint32_t v[32];")),
+        ("epi:rows(out,stats)", find("float* const orow")),
+        ("teardown", find("the peer may still multicast")),
+    ], key=lambda x: x[1])
+    bmarks = None
+else:
+  marks = sorted([
     ("builder:load_rows", find("__device__ __forceinline__ void load_rows")),
     ("builder:touch_rows", find("__device__ __forceinline__ void touch_rows")),
     ("builder:convert", find("__device__ __forceinline__ void convert_store")),
@@ -42,7 +59,16 @@ marks = sorted([
     ("epi:tmem+transpose", find("uint32_t v[32];")),
     ("epi:rows(out,stats)", find("float4 s1 = make_float4")),
     ("teardown", find("the peer may still multicast")),
-], key=lambda x: x[1])
+  ], key=lambda x: x[1])
+# helper functions that live in conv_builders.cuh (conv_wide.cu build): attributed by their own file lines
+try:
+    bsrc = open(src_path.replace(fname, "conv_builders.cuh")).read().split("\n")
+    def bfind(marker):
+        return next(i + 1 for i, l in enumerate(bsrc) if marker in l)
+    bmarks = sorted([("builder:load_rows", bfind("void load_rows")), ("builder:touch_rows", bfind("void touch_rows")),
+                     ("builder:convert", bfind("void convert_store"))], key=lambda x: x[1])
+except (OSError, StopIteration):
+    bmarks = None
 
 
 def region(line):
@@ -80,6 +106,11 @@ for r in data:
     c, x, t = offmap[int(r[0], 16) - base]
     if mode == "regions":
         key = region(x)
+        if bmarks and c and c[0] == "conv_builders.cuh":
+            key = "builder:plan"
+            for n_, l_ in bmarks:
+                if c[1] >= l_:
+                    key = n_
         if c and c[0] == "common.cuh" and 78 <= c[1] <= 113:
             key += " [mbarrier wait]"
     else:
