@@ -48,9 +48,11 @@ PROTOTYPES = {
     "dsep_gn_act_split": [_p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p, _p],
     "dsep_fir_resample": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
     "dsep_fir_resample8": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _i, _p],
+    "dsep_fir_resample_f32": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p],
     "dsep_upfirdn2d": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "dsep_combine": [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p],
     "dsep_add": [_p, _p, _p, _i64, _p],
+    "dsep_im2col3x3": [_p, _i, _i, _i, _i, _i, _p, _p],
     "dsep_attention": [_p, _i, _i, _i, _f, _p, _p, _p],
     "dsep_time_embedding": [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p],
     "dsep_film": [_p, _p, _p, _i, _i, _i, _p, _p],

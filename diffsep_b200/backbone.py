@@ -212,6 +212,15 @@ class NCSNppB200:
         self.t_w1, self.t_b1 = f32(mod(1, "weight")), f32(mod(1, "bias"))
         self.t_w2, self.t_b2 = f32(mod(2, "weight")), f32(mod(2, "bias"))
         self.conv_in = ConvWeight(P[mod(3, "weight")], P[mod(3, "bias")], dev)
+        # the input conv as a 1x1 convolution over im2col rows (dsep_im2col3x3): 9 * ch_in = 54 -> ONE 64-channel
+        # K-block through the fused kernel instead of nine taps of a 6 -> 64 padded plane operand
+        self.conv_in_col = None
+        if self.fuse and self.passes == 2 and cin_align() == 64 and 9 * self.ch_in <= 64 \
+                and int(os.environ.get("DSEP_CONV_IN_COL", "1")):
+            w_in = P[mod(3, "weight")].detach().to(device=dev, dtype=torch.float32)       # [nf, ch_in, 3, 3]
+            w_col = torch.zeros(w_in.shape[0], 64, 1, 1, device=dev, dtype=torch.float32)
+            w_col[:, :9 * self.ch_in, 0, 0] = w_in.permute(0, 2, 3, 1).reshape(w_in.shape[0], 9 * self.ch_in)
+            self.conv_in_col = ConvWeight(w_col, P[mod(3, "bias")], dev)
         self.out_w = f32("output_layer.weight").reshape(self.ch_out, self.ch_in).contiguous()
         self.out_b = f32("output_layer.bias")
 
@@ -482,10 +491,20 @@ class _Plan:
             assert mode != 0 and x1 is None and rb["has_shortcut"]
             xr = ar.f32(B, Ho, Wo, Cin)
             e4 = self.net.passes == 2 and rb["conv0"].cout_pad >= 64
-            a8 = ConvWeight.A8_EXP if e4 else None
-            self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
-                                                       a=a, y=xr, a8_exp=a8))
-            self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st, e4m3=e4)
+            if e4 and int(os.environ.get("DSEP_FIR_F32", "1")):
+                # the FIR pass writes FIR(SiLU(GN0(x))) in fp32 and Conv_0 builds its operand planes itself (same
+                # bytes through HBM as the two planes): it runs on the wide-tile fused kernel like the plain blocks
+                af = ar.f32(B, Ho, Wo, Cin)
+                self.steps.append(lambda: ops.fir_resample_f32(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
+                                                               af, y=xr))
+                self._conv_fused(Ho, Wo, Cin, rb["conv0"], h.t, Cout, af, Cin, None, 0, None, None, 0,
+                                 film=rb["film_off"], stats=h.st)
+                ar.release(af)
+            else:
+                a8 = ConvWeight.A8_EXP if e4 else None
+                self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
+                                                           a=a, y=xr, a8_exp=a8))
+                self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st, e4m3=e4)
             ar.release(a)
             st_h = self._ensure_stats(h)
             sc1, sh1 = self._tables(st_h, Cout, None, 0, Ho * Wo, gam1, bet1)
@@ -555,7 +574,14 @@ class _Plan:
         nres = len(CH_MULT)
         H, W = 256, W0
         h = Act(ar.f32(B, H, W, nf), nf, H, W, self._fused_slot(H, W, nf))
-        self._conv(lambda: self.x_planes, H, W, net.conv_in.cin_pad, net.conv_in, h.t, nf, stats=h.st)
+        if net.conv_in_col is not None:
+            col = ar.f32(B, H, W, 64)
+            # (H, W are rebound below as the levels go by: bind them now)
+            self.steps.append(lambda H=H, W=W, col=col: ops.im2col3x3(self.x_pyramid, B, H, W, ch_in, 64, col))
+            self._conv_fused(H, W, 64, net.conv_in_col, h.t, nf, col, 64, None, 0, None, None, 0, stats=h.st)
+            ar.release(col)
+        else:
+            self._conv(lambda: self.x_planes, H, W, net.conv_in.cin_pad, net.conv_in, h.t, nf, stats=h.st)
         hs = [h]
         pyr_in = None            # running input pyramid (fp32, ch_in channels); level 0 = x_pyramid
         for lvl, level in enumerate(net.down):

@@ -13,8 +13,8 @@ struct PatchPlan {
     uint32_t step;         // elements between rows u and u + 1
     uint32_t inb;          // bit u: row u exists and lies inside the image
     uint32_t smask;        // bit u: row u is stored at all (conv_wide.cu: the second half patch ends after 160 rows)
-    uint32_t krows;        // 30 / 32
-    uint32_t niter;        // 6 / 4 (0: this thread has no rows)
+    uint32_t krows;        // 30 / 32 (conv_wide.cu: 60 / 64)
+    uint32_t niter;        // 6 / 4 (conv_wide.cu: 3 / 2; 0: this thread has no rows)
     uint32_t so;           // index of this thread's 8 channels in the sc / sh tables
     int mode;              // 0 raw (shortcut operand), 1 affine, 2 affine + SiLU
     bool second;           // shortcut K-block (fp16 (hi, lo) planes even in the e4m3 mode)
@@ -37,9 +37,11 @@ __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
 //                 loads right after converting that row and lost a full memory round trip per ROW (1.28 ms for the
 //                 builders alone against 1.11 ms without any prefetch, profiles/conv_r2b.md);
 //   convert_rows — SiLU, (hi, lo) / (hi, e4m3) split, swizzled stores: depends on touch_rows' results only.
-__device__ __forceinline__ void load_rows(float4 (&v)[6][2], const PatchPlan& d) {
+// NR: rows per thread and register set (6 with 8 builder warps, 3 with conv_wide.cu's 16)
+template <int NR>
+__device__ __forceinline__ void load_rows(float4 (&v)[NR][2], const PatchPlan& d) {
 #pragma unroll
-    for (int u = 0; u < 6; ++u) {
+    for (int u = 0; u < NR; ++u) {
         if ((d.inb >> u) & 1u) {
             const float* q = d.src + static_cast<size_t>(u) * d.step;
             ldg_stream8(q, v[u][0], v[u][1]);
@@ -50,7 +52,8 @@ __device__ __forceinline__ void load_rows(float4 (&v)[6][2], const PatchPlan& d)
 // mode 2 (SiLU follows): the affine is pre-scaled by c = -log2(e), so v holds u = c * t and convert_store needs no
 // multiply in front of ex2: y = t / (1 + 2^u) = u * rcp(c + c * 2^u).
 constexpr float kNegLog2e = -1.4426950408889634f;
-__device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d, const float* __restrict__ sc,
+template <int NR>
+__device__ __forceinline__ void touch_rows(float4 (&v)[NR][2], const PatchPlan& d, const float* __restrict__ sc,
                                            const float* __restrict__ sh, float negzero) {
     float k_sc[8], k_sh[8];
     if (d.mode != 0 && sc != nullptr) {
@@ -71,7 +74,7 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[6][2], const PatchPlan& d
         for (int e = 0; e < 8; ++e) { k_sc[e] *= kNegLog2e; k_sh[e] *= kNegLog2e; }
     }
 #pragma unroll
-    for (int u = 0; u < 6; ++u) {
+    for (int u = 0; u < NR; ++u) {
         if ((d.inb >> u) & 1u) {
             v[u][0].x = fmaf(v[u][0].x, k_sc[0], k_sh[0]); v[u][0].y = fmaf(v[u][0].y, k_sc[1], k_sh[1]);
             v[u][0].z = fmaf(v[u][0].z, k_sc[2], k_sh[2]); v[u][0].w = fmaf(v[u][0].w, k_sc[3], k_sh[3]);
@@ -124,27 +127,35 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
     sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
 }
 
-// HALO3: the 10 x 18 patch of a 3x3 conv (6 rows per thread, 30 patch rows apart) — else 8 x 16 (4 rows, 32 apart):
-// compile-time geometry keeps the row / swizzle arithmetic in immediates.
+// One thread's rows of a (half) patch -> both planes: rows r0 + u * KROWS (u < NITER) of the patch part that starts at
+// slot_addr, whose first row has index rbias (mod 8) inside its 1024-byte swizzle atom.  Compile-time geometry keeps
+// the row / swizzle arithmetic in immediates.  MASKED: rows without their smask bit are not stored at all.
+template <bool E4M3, int KROWS, int NITER, bool MASKED, int NR>
+__device__ __forceinline__ void convert_rows_g(const float4 (&v)[NR][2], const PatchPlan& cur, uint32_t slot_addr,
+                                               uint32_t r0, uint32_t jchunk, float a8_lo, uint32_t plane_stride,
+                                               uint32_t rbias) {
+    static_assert(NITER <= NR, "convert_rows_g: register set too small");
+    if (cur.niter == 0u) return;                 // threads beyond the patch (r0 >= KROWS)
+    const bool silu = cur.mode == 2;
+    const uint32_t base = slot_addr + r0 * 128u;
+#pragma unroll
+    for (int u = 0; u < NITER; ++u) {
+        // (r0 + u * KROWS) & 7 == (r0 + (u * KROWS & 7)) & 7: only the low bits of r0 are runtime
+        const uint32_t sw = ((jchunk ^ ((r0 + rbias + ((u * KROWS) & 7u)) & 7u)) << 4);
+        const uint32_t off = base + u * KROWS * 128u + sw;
+        if (MASKED && !((cur.smask >> u) & 1u)) continue;
+        convert_store<E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, off, off + plane_stride, a8_lo);
+    }
+}
+
+// conv_fused.cu's geometry.  HALO3: the 10 x 18 patch of a 3x3 conv (6 rows per thread, 30 patch rows apart) — else
+// 8 x 16 (4 rows, 32 apart).
 template <bool E4M3, bool HALO3, bool MASKED = false>
 __device__ __forceinline__ void convert_rows(const float4 (&v)[6][2], const PatchPlan& cur, uint32_t slot_addr,
                                              uint32_t r0, uint32_t jchunk, float a8_lo,
                                              uint32_t plane_stride = kPatchPlane, uint32_t rbias = 0u) {
-    constexpr int kIter = HALO3 ? 6 : 4;
-    constexpr uint32_t kRows = HALO3 ? 30u : 32u;
-    if (cur.niter == 0u) return;                 // threads beyond the patch (r0 >= 30 in the halo geometry)
-    const bool silu = cur.mode == 2;
-    const uint32_t base = slot_addr + r0 * 128u;
-#pragma unroll
-    for (int u = 0; u < kIter; ++u) {
-        // (r0 + u * kRows) & 7 == (r0 + (u * kRows & 7)) & 7: only the low bits of r0 are runtime
-        // rbias: row index of slot_addr within its 1024-byte swizzle atom (conv_wide.cu's second half patch starts at
-        // row 180 of the plane: 180 & 7 = 4)
-        const uint32_t sw = ((jchunk ^ ((r0 + rbias + ((u * kRows) & 7u)) & 7u)) << 4);
-        const uint32_t off = base + u * kRows * 128u + sw;
-        if (MASKED && !((cur.smask >> u) & 1u)) continue;
-        convert_store<E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, off, off + plane_stride, a8_lo);
-    }
+    convert_rows_g<E4M3, HALO3 ? 30 : 32, HALO3 ? 6 : 4, MASKED, 6>(v, cur, slot_addr, r0, jchunk, a8_lo, plane_stride,
+                                                                   rbias);
 }
 
 }  // namespace dsep

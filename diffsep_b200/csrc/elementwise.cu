@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(256)
 fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, const double* __restrict__ st,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
-                f16x4* __restrict__ r_lo, float4* __restrict__ y, int tiles_w, int tiles_h, float a8_hi,
-                float a8_lo) {
+                f16x4* __restrict__ r_lo, float4* __restrict__ y, float4* __restrict__ af, int tiles_w, int tiles_h,
+                float a8_hi, float a8_lo) {
     using FT = FirTile<MODE>;
     extern __shared__ __align__(16) float s_fir[];
     float4* s_act = reinterpret_cast<float4*>(s_fir);                  // [IH*IW][8 quads]
@@ -259,7 +259,8 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
     const int ih0 = MODE == 1 ? oh0 / 2 - 1 : oh0 * 2 - 1;
     const int iw0 = MODE == 1 ? ow0 / 2 - 1 : ow0 * 2 - 1;
     const int c0 = chunk * 32;
-    const bool xf = st != nullptr && a_hi != nullptr;
+    const bool want_act = a_hi != nullptr || af != nullptr;     // the GroupNorm + SiLU branch (planes and / or fp32)
+    const bool xf = st != nullptr && want_act;
     const bool want_raw = r_hi != nullptr || y != nullptr;
     // the patch loads go out first and stay in flight while 32 threads turn the GroupNorm sums into this chunk's
     // scale / shift (both are one memory round trip; back to back they were ~2 of the ~8 us a block lives)
@@ -304,7 +305,7 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
             const int q = i & 7, pix = i >> 3;
             const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
             float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a_hi != nullptr && ih >= 0 && ih < H && iw >= 0 && iw < W)
+            if (want_act && ih >= 0 && ih < H && iw >= 0 && iw < W)
                 av = xf ? affine_act(raw[k], *reinterpret_cast<const float4*>(s_sc + q * 4),
                                      *reinterpret_cast<const float4*>(s_sh + q * 4), true)
                         : raw[k];
@@ -330,7 +331,7 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
                 for (int d = 0; d < 2; ++d) {
                     const float wgt = (a == 0 ? wy0 : 1.0f - wy0) * (d == 0 ? wx0 : 1.0f - wx0);
                     const int si = ((py + a) * FT::IW + (px + d)) * 8 + q;
-                    if (a_hi != nullptr) {
+                    if (want_act) {
                         const float4 t = s_act[si];
                         acc_a.x = fmaf(wgt, t.x, acc_a.x); acc_a.y = fmaf(wgt, t.y, acc_a.y);
                         acc_a.z = fmaf(wgt, t.z, acc_a.z); acc_a.w = fmaf(wgt, t.w, acc_a.w);
@@ -350,7 +351,7 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
                 for (int d = 0; d < 4; ++d) {
                     const float wgt = wt[a] * wt[d];
                     const int si = ((2 * oy + a) * FT::IW + (2 * ox + d)) * 8 + q;
-                    if (a_hi != nullptr) {
+                    if (want_act) {
                         const float4 t = s_act[si];
                         acc_a.x = fmaf(wgt, t.x, acc_a.x); acc_a.y = fmaf(wgt, t.y, acc_a.y);
                         acc_a.z = fmaf(wgt, t.z, acc_a.z); acc_a.w = fmaf(wgt, t.w, acc_a.w);
@@ -379,6 +380,7 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
         }
         if (r_hi != nullptr) { split4(acc_r, h, l); r_hi[o] = h; r_lo[o] = l; }
         if (y != nullptr) y[o] = acc_r;
+        if (af != nullptr) af[o] = acc_a;
     }
 }
 
@@ -578,7 +580,7 @@ extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, con
 template <int MODE>
 static int launch_fir_tile(const float* x, int B, int H, int W, int C, int groups, const double* st,
                            const float* gamma, const float* beta, float eps, void* a_hi, void* a_lo,
-                           void* r_hi, void* r_lo, float* y, float a8_hi, float a8_lo, cudaStream_t s) {
+                           void* r_hi, void* r_lo, float* y, float* af, float a8_hi, float a8_lo, cudaStream_t s) {
     using FT = FirTile<MODE>;
     static PerDeviceAttr attr;
     const cudaError_t e = set_max_smem_once(attr, fir_tile_kernel<MODE>, FT::kSmemBytes);
@@ -591,23 +593,23 @@ static int launch_fir_tile(const float* x, int B, int H, int W, int C, int group
     dim3 grid(tiles_w * tiles_h, C / 32, B);
     fir_tile_kernel<MODE><<<grid, 256, FT::kSmemBytes, s>>>(x, H, W, C, groups, st, gamma, beta, eps, (f16x4*)a_hi,
                                                             (f16x4*)a_lo, (f16x4*)r_hi, (f16x4*)r_lo, (float4*)y,
-                                                            tiles_w, tiles_h, a8_hi, a8_lo);
+                                                            (float4*)af, tiles_w, tiles_h, a8_hi, a8_lo);
     return check_launch("fir_tile_kernel");
 }
 
 static int fir_resample_impl(const float* x, int B, int H, int W, int C, int mode, int groups,
                              const double* st, const float* gamma, const float* beta, float eps,
                              void* a_hi, void* a_lo, void* r_hi, void* r_lo, float* y, float a8_hi, float a8_lo,
-                             dsep_stream_t stream) {
+                             dsep_stream_t stream, float* af = nullptr) {
     DSEP_REQUIRE(x, "fir_resample: null input");
     DSEP_REQUIRE(mode == 1 || mode == 2, "fir_resample: mode must be 1 (up) or 2 (down)");
     DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && B <= 65535, "fir_resample: empty tensor");
     DSEP_REQUIRE(mode == 1 || (H % 2 == 0 && W % 2 == 0), "fir_resample: down needs even H, W");
-    DSEP_REQUIRE(a_hi || r_hi || y, "fir_resample: no output requested");
+    DSEP_REQUIRE(a_hi || r_hi || y || af, "fir_resample: no output requested");
     cudaStream_t s = (cudaStream_t)stream;
     const int Ho = mode == 1 ? H * 2 : H / 2, Wo = mode == 1 ? W * 2 : W / 2;
     if (C % 32 != 0) {
-        DSEP_REQUIRE(!a_hi && !r_hi && y, "fir_resample: C %% 32 != 0 supports the fp32 output only");
+        DSEP_REQUIRE(!a_hi && !r_hi && !af && y, "fir_resample: C %% 32 != 0 supports the fp32 output only");
         const int64_t total = (int64_t)B * Ho * Wo * C;
         if (mode == 1) fir_scalar_kernel<1><<<grid_for(total), 256, 0, s>>>(x, total, H, W, C, y);
         else fir_scalar_kernel<2><<<grid_for(total), 256, 0, s>>>(x, total, H, W, C, y);
@@ -616,13 +618,13 @@ static int fir_resample_impl(const float* x, int B, int H, int W, int C, int mod
     DSEP_REQUIRE((a_hi == nullptr) == (a_lo == nullptr) && (r_hi == nullptr) == (r_lo == nullptr),
                  "fir_resample: hi/lo planes must come in pairs");
     if (st) {
-        DSEP_REQUIRE(gamma && beta && a_hi, "fir_resample: GroupNorm branch needs gamma, beta and a_hi/a_lo");
+        DSEP_REQUIRE(gamma && beta && (a_hi || af), "fir_resample: GroupNorm branch needs gamma, beta and an output for it");
         int rc = check_gn_shape("fir_resample", C, 0, groups);
         if (rc) return rc;
     }
-    return mode == 1 ? launch_fir_tile<1>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y,
+    return mode == 1 ? launch_fir_tile<1>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, af,
                                           a8_hi, a8_lo, s)
-                     : launch_fir_tile<2>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y,
+                     : launch_fir_tile<2>(x, B, H, W, C, groups, st, gamma, beta, eps, a_hi, a_lo, r_hi, r_lo, y, af,
                                           a8_hi, a8_lo, s);
 }
 
@@ -642,6 +644,16 @@ extern "C" int dsep_fir_resample8(const float* x, int B, int H, int W, int C, in
     DSEP_REQUIRE(a8_exp >= -8 && a8_exp <= 8, "fir_resample8: a8_exp out of range");
     return fir_resample_impl(x, B, H, W, C, mode, groups, st, gamma, beta, eps, a_hi, a_8, r_hi, r_lo, y,
                              ldexpf(1.0f, a8_exp), ldexpf(1.0f, a8_exp + 11), stream);
+}
+
+// The activated branch FIR(SiLU(GN(x))) as fp32 (for a consumer that builds its operand planes itself: the fused
+// convolution with x0 = af and no GroupNorm tables) and / or FIR(x) in y.
+extern "C" int dsep_fir_resample_f32(const float* x, int B, int H, int W, int C, int mode, int groups,
+                                     const double* st, const float* gamma, const float* beta, float eps, float* af,
+                                     float* y, dsep_stream_t stream) {
+    DSEP_REQUIRE(af && st && C % 32 == 0, "fir_resample_f32: needs af, the GroupNorm sums and C %% 32 == 0");
+    return fir_resample_impl(x, B, H, W, C, mode, groups, st, gamma, beta, eps, nullptr, nullptr, nullptr, nullptr, y,
+                             0.f, 0.f, stream, af);
 }
 
 extern "C" int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_x, int up_y, int down_x,
@@ -678,6 +690,42 @@ extern "C" int dsep_combine(const float* pyr, int Cp, const float* w, const floa
     const size_t smem = sizeof(float) * (C * Cp + C);
     combine_kernel<<<grid_for(total), 256, smem, (cudaStream_t)stream>>>(pyr, Cp, w, bias, h, out, total, C);
     return check_launch("combine_kernel");
+}
+
+// ------------------------------------------------------------------ im2col of the network's input convolution
+// The first layer (ncsnpp.py:347-349, conv3x3 of the 2 * (nsrc + 1) = 6 input planes) has K = 54: as a 3x3 conv on the
+// tensor core its channel dimension pads 6 -> 64 and nine taps run (0.98 ms at [32,256,256]); as a 1x1 conv over the
+// im2col rows col[pix][tap * C + c] (54 -> 64) it is ONE 64-channel K-block.  One float4 of a row per thread.
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, int H, int W, int C, int Cp, int64_t total, float4* __restrict__ col) {
+    const int Q = Cp >> 2;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int q = static_cast<int>(e % Q);
+        const int64_t pix = e / Q;
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int64_t b = pix / ((int64_t)W * H);
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = q * 4 + i;
+            v[i] = 0.f;
+            if (k < 9 * C) {
+                const int tap = k / C, c = k - tap * C;
+                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v[i] = __ldg(x + ((b * H + hh) * W + ww) * C + c);
+            }
+        }
+        col[e] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+extern "C" int dsep_im2col3x3(const float* x, int B, int H, int W, int C, int Cp, float* col, dsep_stream_t stream) {
+    DSEP_REQUIRE(x && col, "im2col3x3: null pointer");
+    DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Cp % 4 == 0 && 9 * C <= Cp, "im2col3x3: bad shape (9 * C <= Cp, Cp %% 4 == 0)");
+    const int64_t total = (int64_t)B * H * W * (Cp / 4);
+    im2col3x3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, Cp, total, (float4*)col);
+    return check_launch("im2col3x3_kernel");
 }
 
 extern "C" int dsep_add(const float* a, const float* b, float* y, int64_t n, dsep_stream_t stream) {

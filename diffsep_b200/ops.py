@@ -161,6 +161,12 @@ def fir_resample(x, B, H, W, Cc, mode, groups=0, stats=None, gamma=None, beta=No
          ptr(r.lo) if r else None, ptr(y), stream())
 
 
+def fir_resample_f32(x, B, H, W, Cc, mode, groups, stats, gamma, beta, eps, af, y=None):
+    """af = FIR(SiLU(GN(x))) in fp32 (+ y = FIR(x)): dsep_fir_resample_f32"""
+    call("dsep_fir_resample_f32", ptr(_f32(x, "x")), B, H, W, Cc, mode, groups, ptr(stats), ptr(gamma), ptr(beta),
+         eps, ptr(_f32(af, "af")), ptr(y), stream())
+
+
 def upfirdn2d_planes(x, planes, H, W, up, down, pad, out):
     call("dsep_upfirdn2d", ptr(_f32(x, "x")), planes, H, W, up, up, down, down, pad[0], pad[1], pad[0], pad[1],
          ptr(out), stream())
@@ -170,6 +176,11 @@ def upfirdn2d_planes(x, planes, H, W, up, down, pad, out):
 def combine(pyr, Cp, w, bias, h, out, B, P, Cc):
     call("dsep_combine", ptr(pyr), Cp, ptr(w), ptr(bias), ptr(h), ptr(out), B, P, Cc, stream())
     return out
+
+
+def im2col3x3(x, B, H, W, Cc, Cp, col):
+    call("dsep_im2col3x3", ptr(_f32(x, "x")), B, H, W, Cc, Cp, ptr(_f32(col, "col")), stream())
+    return col
 
 
 def add(a, b, y):

@@ -139,7 +139,9 @@ class ScoreModelNCSNpp(torch.nn.Module):
             Fr=Fr, Wp=Wp,
             frames=f32(B * ns * Fr, LD), dft=f32(B * ns * Fr, LD),
             frames_mix=f32(B * Fr, LD), dft_mix=f32(B * Fr, LD),
-            x_planes=Split.zeros((B, N_BINS, Wp, self.backbone.conv_in.cin_pad), dev),
+            # operand planes of the input conv — not needed when it runs over im2col rows of x_pyr
+            x_planes=(None if self.backbone.conv_in_col is not None
+                      else Split.zeros((B, N_BINS, Wp, self.backbone.conv_in.cin_pad), dev)),
             x_pyr=f32(B, N_BINS, Wp, self.ch_in),
             spec_out=f32(B * ns * Fr, LD), frames_out=f32(B * ns * Fr, LD),
             score=f32(B, ns, T),
@@ -216,7 +218,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         else:
             ops.stft_frames(mix, self.window, B, 1, T, Fr, bf["frames_mix"])
             ops.sgemm(bf["frames_mix"], LD, self.basis_fwd, LD, bf["dft_mix"], LD, B * Fr, LD, LD)
-            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, ns + 1, bf["x_planes"].shape[-1], self.spec_factor,
+            ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, ns + 1, self.backbone.conv_in.cin_pad, self.spec_factor,
                           self.spec_abs_exponent,
                           bf["x_pyr"], bf["x_planes"])
             self._mix_cache = mix_key if self._mix_cache_on else None
@@ -228,7 +230,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         Fr, Wp = bf["Fr"], bf["Wp"]
         ops.stft_frames(xt, self.window, B, ns, T, Fr, bf["frames"])
         ops.sgemm(bf["frames"], LD, self.basis_fwd, LD, bf["dft"], LD, B * ns * Fr, LD, LD)
-        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, bf["x_planes"].shape[-1], self.spec_factor,
+        ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, self.backbone.conv_in.cin_pad, self.spec_factor,
                       self.spec_abs_exponent,
                       bf["x_pyr"], bf["x_planes"])
         if film_row is not None:      # one row for the whole batch (uniform time); a no-op when replay already set it

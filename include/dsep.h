@@ -160,6 +160,12 @@ int dsep_fir_resample8(const float* x, int B, int H, int W, int C, int mode, int
                        const double* st, const float* gamma, const float* beta, float eps,
                        void* a_hi, void* a_8, void* r_hi, void* r_lo, float* y, int a8_exp,
                        dsep_stream_t stream);
+/* Same resampling with the activated branch in fp32: af = FIR(SiLU(GN(x))) [B,Ho,Wo,C] (and optionally y = FIR(x)),
+ * for a consumer that builds its operand planes itself — the up / down ResBlock's Conv_0 then takes af as x0 of
+ * dsep_conv2d_fused8 (no GroupNorm tables, no activation) and runs on the wide-tile kernel like every other conv. */
+int dsep_fir_resample_f32(const float* x, int B, int H, int W, int C, int mode, int groups, const double* st,
+                          const float* gamma, const float* beta, float eps, float* af, float* y,
+                          dsep_stream_t stream);
 /* Drop-in for the reference's own FFI signature on its own layout: in [planes, H, W] fp32,
  * kernel fixed to outer([1,3,3,1])/16*up^2; supports exactly the two calls the model makes
  * (up=2,down=1,pad=(2,1)) and (up=1,down=2,pad=(1,1)); anything else -> DSEP_ERR_UNSUPPORTED.
@@ -173,6 +179,11 @@ int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_x, int up_y
 int dsep_combine(const float* pyr, int Cp, const float* w, const float* bias, const float* h,
                  float* out, int B, int P, int C, dsep_stream_t stream);
 /* y = a + b (fp32, n elements): pyramid accumulation (ncsnpp.py:440). */
+/* im2col rows of a 3x3 / pad 1 convolution with few input channels: x [B,H,W,C] fp32 -> col [B,H,W,Cp] fp32,
+ * col[pix][tap * C + c] = x[pix + tap offset][c] (zero outside the image and for columns >= 9 * C; tap = ky * 3 + kx).
+ * The network's input conv (ncsnpp.py:347-349, C = 6) then runs as a 1x1 convolution with ONE 64-channel K-block
+ * (dsep_conv2d_fused8 with x0 = col, no GroupNorm tables) instead of nine taps of a 6 -> 64 padded operand. */
+int dsep_im2col3x3(const float* x, int B, int H, int W, int C, int Cp, float* col, dsep_stream_t stream);
 int dsep_add(const float* a, const float* b, float* y, int64_t n, dsep_stream_t stream);
 
 /* ---- attention ---------------------------------------------------------------------------

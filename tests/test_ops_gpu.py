@@ -386,6 +386,88 @@ def test_conv2d_wide_tiles(shape):
     assert rel_l2(stats[..., 1].cpu(), (got * got).sum(dim=(2, 3))) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 24, 6), (1, 16, 8, 7), (3, 5, 9, 2)])
+def test_im2col3x3_and_input_conv_as_1x1(shape):
+    """dsep_im2col3x3: col[pix][tap * C + c] of a 3x3 / pad 1 convolution (bit-exact gather, zero borders and zero
+    padding columns), and the network's input conv computed from it as a 1x1 product equals F.conv2d."""
+    ops = _ops()
+    B, H, W, C = shape
+    g = cases.gen(sum(shape))
+    x = torch.randn(B, C, H, W, generator=g)
+    col = torch.full((B, H, W, 64), float("nan"), device=DEV)
+    ops.im2col3x3(cl(x), B, H, W, C, 64, col)
+    torch.cuda.synchronize()
+    ref = F.unfold(x, 3, padding=1).reshape(B, C, 9, H, W).permute(0, 3, 4, 2, 1).reshape(B, H, W, 9 * C)
+    assert torch.equal(col[..., :9 * C].cpu(), ref)
+    assert torch.equal(col[..., 9 * C:].cpu(), torch.zeros(B, H, W, 64 - 9 * C))
+    w = torch.randn(16, C, 3, 3, generator=g)
+    w_col = w.permute(0, 2, 3, 1).reshape(16, 9 * C)
+    got = torch.einsum("bhwk,ok->bohw", col[..., :9 * C].cpu().double(), w_col.double())
+    assert rel_l2(got, F.conv2d(x.double(), w.double(), padding=1)) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 6, 128), (1, 48, 16, 6, 64), (1, 256, 64, 6, 64)])
+def test_input_conv_over_im2col_rows(shape):
+    """The network's input conv the way the plan runs it in passes = 2: dsep_im2col3x3 + the fused 1x1 convolution with
+    a raw fp32 operand (no GroupNorm tables, no activation, ONE 64-channel K-block), weights rearranged to
+    [Cout, tap * C + c], vs F.conv2d in float64."""
+    ops = _ops()
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, C, Cout = shape
+    g = cases.gen(sum(shape) + 17)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Cout, C, 3, 3, generator=g) / math.sqrt(C * 9)
+    b1 = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv2d(x.double(), w.double(), b1.double(), padding=1)
+    col = torch.empty(B, H, W, 64, device=DEV)
+    ops.im2col3x3(cl(x), B, H, W, C, 64, col)
+    w_col = torch.zeros(Cout, 64, 1, 1)
+    w_col[:, :9 * C, 0, 0] = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C)
+    cw = ConvWeight(w_col, b1, DEV)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    stats = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    ops.conv2d_fused(B, H, W, 64, cw.planes8(), cw.cout_pad, 1, out, Cout, x0=col, C0=64, act=0, bias=cw.bias,
+                     acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel, a8_exp=cw.A8_EXP)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(out), ref) < 3e-5
+    assert rel_l2(stats[..., 0].cpu(), nchw(out).double().sum(dim=(2, 3))) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 12, 128, 1), (1, 64, 32, 64, 2), (2, 32, 16, 256, 2), (1, 8, 8, 128, 1)])
+def test_fir_resample_f32_activated_branch(shape):
+    """dsep_fir_resample_f32: FIR(SiLU(GN(x))) and FIR(x) in fp32 (the up / down ResBlock's Conv_0 / shortcut inputs
+    when Conv_0 builds its own operand planes), vs float64 (up_or_down_sampling.py:206-273 restated with F.conv2d)."""
+    ops = _ops()
+    B, H, W, C, mode = shape
+    g = cases.gen(sum(shape) + 13)
+    x = torch.randn(B, C, H, W, generator=g) * 1.1 - 0.05
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    a = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    a = a * torch.sigmoid(a)
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    k2 = torch.outer(k1, k1)
+    k2 = k2 / k2.sum()
+
+    def fir(t):
+        if mode == 2:
+            o = F.conv2d(F.pad(t, (1, 1, 1, 1)).reshape(B * C, 1, H + 2, W + 2), k2[None, None], stride=2)
+            return o.reshape(B, C, H // 2, W // 2)
+        z = torch.zeros(B * C, 1, 2 * H, 2 * W, dtype=torch.float64)
+        z[:, :, ::2, ::2] = t.reshape(B * C, 1, H, W)
+        return F.conv2d(F.pad(z, (2, 1, 2, 1)), (k2 * 4).flip(0, 1)[None, None]).reshape(B, C, 2 * H, 2 * W)
+    Ho, Wo = (2 * H, 2 * W) if mode == 1 else (H // 2, W // 2)
+    d0 = cl(x)
+    st0 = torch.empty(B, C, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, C, B, H * W, st0)
+    af = torch.full((B, Ho, Wo, C), float("nan"), device=DEV)
+    y = torch.full((B, Ho, Wo, C), float("nan"), device=DEV)
+    ops.fir_resample_f32(d0, B, H, W, C, mode, 32, st0, gamma.to(DEV), beta.to(DEV), 1e-6, af, y=y)
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(af), fir(a)) < 2e-6
+    assert rel_l2(nchw(y), fir(x.double())) < 1e-6
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 12, 128, 128, 1), (1, 64, 32, 128, 256, 2), (1, 32, 16, 256, 128, 2)])
 def test_conv2d_e4m3_corrections_from_fir_planes(shape):
     """The up / down ResBlocks' Conv_0 in passes = 2: dsep_fir_resample8 writes FIR(SiLU(GN(x))) as (fp16 hi,
