@@ -40,6 +40,18 @@ __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
 // NR: rows per thread and register set (6 with 8 builder warps, 3 with conv_wide.cu's 16)
 template <int NR>
 __device__ __forceinline__ void load_rows(float4 (&v)[NR][2], const PatchPlan& d) {
+    // rows that are not loaded (outside the image: the conv pads the ACTIVATED tensor with zeros) are zero-filled here,
+    // and stay zero through touch_rows (skipped for them) and convert_store (SiLU(0) = 0, both planes of 0 are 0) — so
+    // the row body needs no per-row selects.  Interior tiles (every row loaded) skip the fill with one branch.
+    if (d.inb != (1u << d.niter) - 1u) {
+#pragma unroll
+        for (int u = 0; u < NR; ++u) {
+            if (!((d.inb >> u) & 1u)) {
+                v[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
 #pragma unroll
     for (int u = 0; u < NR; ++u) {
         if ((d.inb >> u) & 1u) {
@@ -91,8 +103,7 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[NR][2], const PatchPlan& 
 template <bool E4M3>
 __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, bool silu, uint32_t dst_hi,
                                               uint32_t dst_2, float a8_lo) {
-    // rows outside the image are computed like the others (on whatever the registers hold) and zeroed by selects at
-    // the end: one straight-line body per row instead of a branch around it
+    // rows outside the image arrive as zeros (load_rows) and come out as zeros: one straight-line body per row
     uint32_t hi[4], lo[4];
     float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     if (silu) {
@@ -121,8 +132,7 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
 #pragma unroll
         for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { hi[e] = inside ? hi[e] : 0u; lo[e] = inside ? lo[e] : 0u; }
+    (void)inside;
     sts128(dst_hi, hi[0], hi[1], hi[2], hi[3]);
     sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
 }

@@ -696,15 +696,17 @@ extern "C" int dsep_combine(const float* pyr, int Cp, const float* w, const floa
 // The first layer (ncsnpp.py:347-349, conv3x3 of the 2 * (nsrc + 1) = 6 input planes) has K = 54: as a 3x3 conv on the
 // tensor core its channel dimension pads 6 -> 64 and nine taps run (0.98 ms at [32,256,256]); as a 1x1 conv over the
 // im2col rows col[pix][tap * C + c] (54 -> 64) it is ONE 64-channel K-block.  One float4 of a row per thread.
+template <int CT, int CPT>      // compile-time (C, Cp) for the network's shape (6, 64); (0, 0): run-time values
 __global__ void __launch_bounds__(256)
-im2col3x3_kernel(const float* __restrict__ x, int H, int W, int C, int Cp, int64_t total, float4* __restrict__ col) {
+im2col3x3_kernel(const float* __restrict__ x, int H, int W, int C_, int Cp_, int64_t total, float4* __restrict__ col) {
+    const int C = CT ? CT : C_, Cp = CPT ? CPT : Cp_;
     const int Q = Cp >> 2;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int q = static_cast<int>(e % Q);
-        const int64_t pix = e / Q;
-        const int w = static_cast<int>(pix % W);
-        const int h = static_cast<int>((pix / W) % H);
-        const int64_t b = pix / ((int64_t)W * H);
+        const uint32_t pix = static_cast<uint32_t>(e / Q);          // B * H * W < 2^32
+        const uint32_t row = pix / static_cast<uint32_t>(W);        // b * H + h
+        const int w = static_cast<int>(pix - row * static_cast<uint32_t>(W));
+        const int h = static_cast<int>(row % static_cast<uint32_t>(H));
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -712,8 +714,10 @@ im2col3x3_kernel(const float* __restrict__ x, int H, int W, int C, int Cp, int64
             v[i] = 0.f;
             if (k < 9 * C) {
                 const int tap = k / C, c = k - tap * C;
-                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v[i] = __ldg(x + ((b * H + hh) * W + ww) * C + c);
+                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                const int hh = h + dy, ww = w + dx;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    v[i] = __ldg(x + (static_cast<int64_t>(pix) + dy * W + dx) * C + c);
             }
         }
         col[e] = make_float4(v[0], v[1], v[2], v[3]);
@@ -724,7 +728,12 @@ extern "C" int dsep_im2col3x3(const float* x, int B, int H, int W, int C, int Cp
     DSEP_REQUIRE(x && col, "im2col3x3: null pointer");
     DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Cp % 4 == 0 && 9 * C <= Cp, "im2col3x3: bad shape (9 * C <= Cp, Cp %% 4 == 0)");
     const int64_t total = (int64_t)B * H * W * (Cp / 4);
-    im2col3x3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, Cp, total, (float4*)col);
+    DSEP_REQUIRE((int64_t)B * H * W < (int64_t(1) << 32), "im2col3x3: tensor too large");
+    const int blocks = grid_for(total, 256, 148 * 64);
+    if (C == 6 && Cp == 64)
+        im2col3x3_kernel<6, 64><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, H, W, C, Cp, total, (float4*)col);
+    else
+        im2col3x3_kernel<0, 0><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, H, W, C, Cp, total, (float4*)col);
     return check_launch("im2col3x3_kernel");
 }
 
