@@ -353,7 +353,12 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    from diffsep_b200 import _lib
+    n_wide = _lib.load().dsep_conv_wide_launches()
     ms = time_it(run)
+    # which kernel the dispatch picked for this shape (conv_wide.cu: 8 x 32 pixel tiles on the MMA's N side)
+    kname = ("conv_wide_kernel" if _lib.load().dsep_conv_wide_launches() > n_wide
+             else ("conv_fused_kernel<128>" if bb.fuse else "conv_tc_kernel<128, halo>"))
     # for reference: the same convolution fed with ready-made operand planes (no prologue, no statistics)
     ap = ops.Split.empty((B, H, W, Cc), dev)
     ops.split_f16(x, ap)
@@ -367,7 +372,7 @@ def dominant_kernel_roofline(model, dev, peaks, passes):
     tf = ROOT / "profiles" / "conv_traffic.json"      # dram bytes per launch from the committed ncu --set full capture
     if tf.exists() and B == 32:
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-    return {"bound": "tensor", "kernel": "conv_tc_kernel<128, halo> (3x3, 128->128, 256x256, batch %d): %s" % (B, variant),
+    return {"bound": "tensor", "kernel": "%s (3x3, 128->128, 256x256, batch %d): %s" % (kname, B, variant),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback",
             "ms_per_launch": ms, "algorithmic_gflop_per_launch": flops / 1e9, "mma_passes": passes,

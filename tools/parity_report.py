@@ -101,8 +101,10 @@ with sdes.injected_noise(noises):
     got, nfe, im = model.get_pc_sampler("reverse_diffusion", "ald2", mix, N=5, corrector_steps=1, snr=0.5,
                                         denoise=True, intermediate=True)()
 for i, ((gx, _), (wx, _)) in enumerate(zip(im, im_w)):
-    add(f"network-driven PC sampler nf=64, state after corrector of step {i + 1}/5", "CPU oracle sampler", rel(gx.cpu(), wx), 1e-4)
-add("network-driven PC sampler nf=64, final estimate (10 evaluations)", "CPU oracle sampler", rel(got.cpu(), want), 1e-4)
+    add(f"network-driven PC sampler nf=64, N=5, default mode, FREE-RUNNING state after corrector of step {i + 1}/5",
+        "CPU oracle sampler", rel(gx.cpu(), wx), 4e-4)
+add("network-driven PC sampler nf=64, N=5, default mode, free-running final estimate (10 evaluations)",
+    "CPU oracle sampler", rel(got.cpu(), want), 4e-4)
 
 print("| what | against | rel-L2 error | tolerance in tests |\n|---|---|---:|---:|")
 for what, against, err, tol in rows:
