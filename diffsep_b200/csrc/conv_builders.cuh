@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
 //                 of these loads on the same scoreboard; a consumer that waits for "its" loads therefore waits for
 //                 everything in flight on that scoreboard.  The first prefetching version re-issued each row's
 //                 loads right after converting that row and lost a full memory round trip per ROW (1.28 ms for the
-//                 builders alone against 1.11 ms without any prefetch, profiles/conv_r2b.md);
+//                 builders alone against 1.11 ms without any prefetch);
 //   convert_rows — SiLU, (hi, lo) / (hi, e4m3) split, swizzled stores: depends on touch_rows' results only.
 // NR: rows per thread and register set (6 with 8 builder warps, 3 with conv_wide.cu's 16)
 template <int NR>

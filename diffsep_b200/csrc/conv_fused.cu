@@ -5,7 +5,7 @@
 //
 // Same arithmetic, operand layouts and barriers-by-name as conv_tc_kernel<NT, halo> (conv_tc.cu), which this
 // kernel replaces for Cout >= 64 whenever the main operand is built in-kernel.  What changed, and why
-// (profiles/conv_modes_r2a.md): in the 2-unit mode (fp16 hi*hi + one e4m3 product for both corrections) the
+// (DESIGN.md section 5): in the 2-unit mode (fp16 hi*hi + one e4m3 product for both corrections) the
 // tensor core needs 0.74 ms for the level-0 conv but the 8 worker warps that both BUILT the operand patches and
 // RAN the epilogue needed 1.11 ms on their own — issue slots 38 % used, the rest exposed latency: each patch's
 // global loads were issued and immediately waited for, and the epilogue's TMEM / shared / global round trips

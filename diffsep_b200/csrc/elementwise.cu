@@ -430,7 +430,7 @@ fir_scalar_kernel(const float* __restrict__ x, int64_t total_out, int H, int W, 
 // out[b,p,c] = h[b,p,c] + bias[c] + sum_k w[c,k] * pyr[b,p,k]
 // weights are staged transposed, s_w[k][c]: a warp reads 32 consecutive channel quads of one k with one
 // conflict-free LDS.128 per lane (the [c][k] order put the lanes' words 24 floats apart: 8-way bank conflicts,
-// 1.5 TB/s; profiles/membound_r02.md)
+// 1.5 TB/s; profiles/membound_r2a.md)
 __global__ void __launch_bounds__(256)
 combine_kernel(const float* __restrict__ pyr, int Cp, const float* __restrict__ w,
                const float* __restrict__ bias, const float* __restrict__ h, float* __restrict__ out,
