@@ -20,6 +20,14 @@ struct PatchPlan {
     bool second;           // shortcut K-block (fp16 (hi, lo) planes even in the e4m3 mode)
 };
 
+// d = a * b + c with fp16 a, b and fp32 c, d (sm_100 mixed-precision FMA, SASS FHFMA): y - hi in ONE instruction
+// instead of a half -> float conversion and a subtraction (exact either way: both products are exact in fp32)
+__device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
     uint16_t r;
     asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
@@ -100,9 +108,11 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[NR][2], const PatchPlan& 
 // planes.  silu: the values are u = -log2(e) * t and y = t / (1 + 2^u) = u * rcp(c + c 2^u) (ex2.approx.ftz +
 // rcp.approx.ftz, no range fix-ups).  E4M3: second plane = [A_lo8 x 8 | A_hi8 x 8] with A_hi8 converted straight from
 // the packed fp16 pairs (the host passes a8_exp = 0) and A_lo8 = e4m3(lo * a8_lo); else the fp16 lo plane.
-template <bool E4M3>
+// SILU: 1 / 0 = known at compile time (no copy of the row in front of a run-time branch), -1 = the `silu` argument.
+template <bool E4M3, int SILU = -1>
 __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, bool silu, uint32_t dst_hi,
                                               uint32_t dst_2, float a8_lo) {
+    if (SILU >= 0) silu = SILU != 0;
     // rows outside the image arrive as zeros (load_rows) and come out as zeros: one straight-line body per row
     uint32_t hi[4], lo[4];
     float y[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -116,13 +126,15 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
         }
     }
     if (E4M3) {
+        // a8_lo = 2^(11 + a8_exp): l = (y - hi) * a8_lo = y * a8_lo - hi * a8_lo, the second term folded into an FHFMA
+        // with the fp16 constant -a8_lo (exact: power of two; the dispatch admits a8_exp = 0 only, -2048 is 0xE800)
         float l[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(y[2 * e + 1]), "f"(y[2 * e]));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
-            l[2 * e] = (y[2 * e] - b.x) * a8_lo;
-            l[2 * e + 1] = (y[2 * e + 1] - b.y) * a8_lo;
+            const uint16_t h0 = static_cast<uint16_t>(hi[e] & 0xFFFFu), h1 = static_cast<uint16_t>(hi[e] >> 16);
+            l[2 * e] = fma_f32_f16(h0, static_cast<uint16_t>(0xE800u), y[2 * e] * a8_lo);
+            l[2 * e + 1] = fma_f32_f16(h1, static_cast<uint16_t>(0xE800u), y[2 * e + 1] * a8_lo);
         }
         lo[0] = e4m3x4(l[0], l[1], l[2], l[3]);
         lo[1] = e4m3x4(l[4], l[5], l[6], l[7]);
@@ -130,7 +142,13 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
         lo[3] = e4m3x2_from_f16x2(hi[2]) | (e4m3x2_from_f16x2(hi[3]) << 16);
     } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split2_f16(y[2 * e], y[2 * e + 1], hi[e], lo[e]);
+        for (int e = 0; e < 4; ++e) {      // (hi, lo) fp16 pairs; lo = y - hi by FHFMA (hi * -1 + y)
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(y[2 * e + 1]), "f"(y[2 * e]));
+            const uint16_t h0 = static_cast<uint16_t>(hi[e] & 0xFFFFu), h1 = static_cast<uint16_t>(hi[e] >> 16);
+            const float d0 = fma_f32_f16(h0, static_cast<uint16_t>(0xBC00u), y[2 * e]);
+            const float d1 = fma_f32_f16(h1, static_cast<uint16_t>(0xBC00u), y[2 * e + 1]);
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[e]) : "f"(d1), "f"(d0));
+        }
     }
     (void)inside;
     sts128(dst_hi, hi[0], hi[1], hi[2], hi[3]);
@@ -140,7 +158,7 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
 // One thread's rows of a (half) patch -> both planes: rows r0 + u * KROWS (u < NITER) of the patch part that starts at
 // slot_addr, whose first row has index rbias (mod 8) inside its 1024-byte swizzle atom.  Compile-time geometry keeps
 // the row / swizzle arithmetic in immediates.  MASKED: rows without their smask bit are not stored at all.
-template <bool E4M3, int KROWS, int NITER, bool MASKED, int NR>
+template <bool E4M3, int KROWS, int NITER, bool MASKED, int NR, int SILU = -1>
 __device__ __forceinline__ void convert_rows_g(const float4 (&v)[NR][2], const PatchPlan& cur, uint32_t slot_addr,
                                                uint32_t r0, uint32_t jchunk, float a8_lo, uint32_t plane_stride,
                                                uint32_t rbias) {
@@ -154,7 +172,7 @@ __device__ __forceinline__ void convert_rows_g(const float4 (&v)[NR][2], const P
         const uint32_t sw = ((jchunk ^ ((r0 + rbias + ((u * KROWS) & 7u)) & 7u)) << 4);
         const uint32_t off = base + u * KROWS * 128u + sw;
         if (MASKED && !((cur.smask >> u) & 1u)) continue;
-        convert_store<E4M3>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, off, off + plane_stride, a8_lo);
+        convert_store<E4M3, SILU>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, off, off + plane_stride, a8_lo);
     }
 }
 

@@ -215,9 +215,11 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         // ---------------------------------------------------------------------- patch builders
         asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const int wtid = static_cast<int>(threadIdx.x) - 128;
-        const uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
-        const uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
-        const uint32_t a_ring = smem_u32(stage_base);
+        uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
+        uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
+        uint32_t a_ring = smem_u32(stage_base);
+        // opaque to ptxas: it otherwise recomputes all three from %tid / the shared-memory window per patch ROW
+        asm volatile("" : "+r"(jchunk), "+r"(r0), "+r"(a_ring));
         const bool skip = (p.debug & 2) != 0;
         const float a8_lo = p.a8_lo;
 
@@ -261,9 +263,25 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
             pix1 = (g_bs * p.H + h0 + py1) * p.W + w0 + px1;
         };
         if (g_valid) retile();
-        struct Half { PatchPlan d; uint32_t off; uint32_t rbias; };     // + where the half lies in its plane
-        auto next_plan = [&](Half& hp) {            // plan of (g_item, g_pi, g_half), then advance
-            PatchPlan& d = hp.d;
+        // A plan is kept COMPACT between its uses — source pointer + row step (dead once the loads are issued), table
+        // index, and one word of bits: in-image mask (6) | stored-row mask (6) << 8 | form << 16 | half << 18 — and
+        // expanded into a PatchPlan only where a helper wants one: with two full plans live across the row bodies the
+        // builders sat at their register cap and ptxas rematerialised thread indices and the shared-memory base per
+        // ROW (~15 of ~110 instructions).
+        struct Plan { const float* src; uint32_t step, so, bits; };
+        constexpr uint32_t kFormHalo = 0u, kFormPlain = 1u, kFormShort = 2u;      // 3x3 main, 1x1 main, fp16 shortcut
+        auto expand = [&](const Plan& q) {
+            PatchPlan d;
+            const uint32_t form = (q.bits >> 16) & 3u;
+            d.src = q.src; d.step = q.step; d.so = q.so;
+            d.inb = q.bits & 63u; d.smask = (q.bits >> 8) & 63u;
+            d.krows = form == kFormHalo ? 30u : 32u;
+            d.niter = form == kFormHalo ? (act3 ? 6u : 0u) : 4u;
+            d.second = form == kFormShort;
+            d.mode = form == kFormShort ? 0 : (p.fact ? 2 : 1);
+            return d;
+        };
+        auto next_plan = [&](Plan& q) {            // plan of (g_item, g_pi, g_half), then advance
             const bool second = g_pi < p.kblocks2;
             const bool halo3 = !second && p.taps == 9;
             const int kb = second ? g_pi : g_pi - p.kblocks2;
@@ -273,18 +291,14 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
             const int C0 = second ? p.gC0 : p.fC0, C1 = second ? p.gC1 : p.fC1;
             const float* src; int cs, cl;
             if (c < C0) { src = x0; cs = C0; cl = c; } else { src = x1; cs = C1; cl = c - C0; }
-            d.krows = halo3 ? 30u : 32u;
-            d.niter = halo3 ? (act3 ? 6u : 0u) : 4u;
             const int pix = halo3 ? pix3 + g_half * 18 * p.W : pix1 + g_half * 16 * p.W;
-            d.src = src + (static_cast<long long>(pix) * cs + cl);
-            d.step = static_cast<uint32_t>((halo3 ? 3 : 4) * p.W * cs);
-            d.inb = halo3 ? (inb3 >> (6 * g_half)) & 63u : inb1;
-            d.smask = halo3 ? (sm3 >> (6 * g_half)) & 63u : 0xFu;
-            d.so = static_cast<uint32_t>(g_bs * (C0 + C1) + c);
-            d.second = second;
-            d.mode = second ? 0 : (p.fact ? 2 : 1);
-            hp.off = static_cast<uint32_t>(g_half) * (halo3 ? Cfg::kHalfRows3 : Cfg::kHalfRows1) * 128u;
-            hp.rbias = halo3 ? static_cast<uint32_t>(g_half) * (Cfg::kHalfRows3 & 7u) : 0u;
+            q.src = src + (static_cast<long long>(pix) * cs + cl);
+            q.step = static_cast<uint32_t>((halo3 ? 3 : 4) * p.W * cs);
+            q.so = static_cast<uint32_t>(g_bs * (C0 + C1) + c);
+            const uint32_t inb = halo3 ? (inb3 >> (6 * g_half)) & 63u : inb1;
+            const uint32_t smask = halo3 ? (sm3 >> (6 * g_half)) & 63u : 0xFu;
+            const uint32_t form = halo3 ? kFormHalo : (second ? kFormShort : kFormPlain);
+            q.bits = inb | (smask << 8) | (form << 16) | (static_cast<uint32_t>(g_half) << 18);
             if (++g_half == 2) {
                 g_half = 0;
                 if (++g_pi == total_patches) {
@@ -299,17 +313,33 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         // two register sets: while one half patch is converted out of set X, the loads of the following one are in
         // flight into set Y, and vice versa (conv_builders.cuh: load_rows / touch_rows and why they are ordered so)
         float4 vx[6][2], vy[6][2];
-        Half hx, hy;
+        Plan qx, qy;
         int as_ = 0, halves_done = 0;
         uint32_t aph = 0;
         const float negzero = -(p.acc_scale * 0.0f);
+        const bool silu = p.fact != 0;
         auto wait_slot = [&]() { if (halves_done == 0) mbar_wait(&aempty[as_], aph ^ 1u); };
-        auto build = [&](const float4 (&v)[6][2], const Half& cur) {
-            const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage + cur.off;
-            const bool halo3 = cur.d.krows == 30u;
-            if (cur.d.second) convert_rows<false, false, true>(v, cur.d, slot, r0, jchunk, 0.f, Cfg::kPlaneBytes, 0u);
-            else if (halo3) convert_rows<true, true, true>(v, cur.d, slot, r0, jchunk, a8_lo, Cfg::kPlaneBytes, cur.rbias);
-            else convert_rows<true, false, true>(v, cur.d, slot, r0, jchunk, a8_lo, Cfg::kPlaneBytes, 0u);
+        auto load = [&](float4 (&v)[6][2], const Plan& q) { const PatchPlan d = expand(q); load_rows(v, d); };
+        auto touch = [&](float4 (&v)[6][2], const Plan& q) {
+            const PatchPlan d = expand(q);
+            touch_rows(v, d, p.fsc, p.fsh, negzero);
+        };
+        auto build = [&](const float4 (&v)[6][2], const Plan& q) {
+            const PatchPlan d = expand(q);
+            const uint32_t form = (q.bits >> 16) & 3u, half = (q.bits >> 18) & 1u;
+            const uint32_t off = half * (form == kFormHalo ? Cfg::kHalfRows3 : Cfg::kHalfRows1) * 128u;
+            const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage + off;
+            constexpr uint32_t PS = Cfg::kPlaneBytes;
+            if (form == kFormShort) {
+                convert_rows_g<false, 32, 4, true, 6, 0>(v, d, slot, r0, jchunk, 0.f, PS, 0u);
+            } else if (form == kFormHalo) {
+                const uint32_t rbias = half * (Cfg::kHalfRows3 & 7u);
+                if (silu) convert_rows_g<true, 30, 6, true, 6, 1>(v, d, slot, r0, jchunk, a8_lo, PS, rbias);
+                else convert_rows_g<true, 30, 6, true, 6, 0>(v, d, slot, r0, jchunk, a8_lo, PS, rbias);
+            } else {
+                if (silu) convert_rows_g<true, 32, 4, true, 6, 1>(v, d, slot, r0, jchunk, a8_lo, PS, 0u);
+                else convert_rows_g<true, 32, 4, true, 6, 0>(v, d, slot, r0, jchunk, a8_lo, PS, 0u);
+            }
             // each builder warp publishes its share of each half (afull counts 8 warps x 2 halves)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tensor core)
             __syncwarp();
@@ -321,25 +351,25 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         };
         bool has_x = g_valid, has_y = false;
         if (has_x) {
-            next_plan(hx);
-            load_rows(vx, hx.d);
+            next_plan(qx);
+            load(vx, qx);
             has_y = g_valid;
-            if (has_y) next_plan(hy);
+            if (has_y) next_plan(qy);
         }
         while (has_x) {
-            touch_rows(vx, hx.d, p.fsc, p.fsh, negzero);
+            touch(vx, qx);
             wait_slot();
-            if (has_y) load_rows(vy, hy.d);
-            build(vx, hx);
+            if (has_y) load(vy, qy);
+            build(vx, qx);
             has_x = g_valid;
-            if (has_x) next_plan(hx);
+            if (has_x) next_plan(qx);
             if (!has_y) break;
-            touch_rows(vy, hy.d, p.fsc, p.fsh, negzero);
+            touch(vy, qy);
             wait_slot();
-            if (has_x) load_rows(vx, hx.d);
-            build(vy, hy);
+            if (has_x) load(vx, qx);
+            build(vy, qy);
             has_y = g_valid;
-            if (has_y) next_plan(hy);
+            if (has_y) next_plan(qy);
         }
     } else {
         // ---------------------------------------------------------------------- epilogue (4 warps)
