@@ -328,7 +328,8 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
             const PatchPlan d = expand(q);
             const uint32_t form = (q.bits >> 16) & 3u, half = (q.bits >> 18) & 1u;
             const uint32_t off = half * (form == kFormHalo ? Cfg::kHalfRows3 : Cfg::kHalfRows1) * 128u;
-            const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage + off;
+            uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage + off;
+            asm volatile("" : "+r"(slot));      // once per half patch, not per row
             constexpr uint32_t PS = Cfg::kPlaneBytes;
             if (form == kFormShort) {
                 convert_rows_g<false, 32, 4, true, 6, 0>(v, d, slot, r0, jchunk, 0.f, PS, 0u);
