@@ -1113,7 +1113,12 @@ static int conv_dispatch(const dsep_conv_args* g, float corr_rel, int a8_exp, ds
     DSEP_REQUIRE(Cin2 == 0 || ((g->a2_hi || short_fused) && g->w2_hi &&
                                (passes == 1 || ((g->a2_lo || short_fused) && g->w2_lo))),
                  "conv2d_tc: fused 1x1 operand (Cin2=%d) needs its activation and weight planes", Cin2);
-    const int NT = Cout_pad == 16 ? 16 : (Cout_pad % 128 == 0 ? 128 : 64);
+    int NT = Cout_pad == 16 ? 16 : (Cout_pad % 128 == 0 ? 128 : 64);
+    // small maps (the 4x4 / 8x8 levels: 4 - 16 pixel tiles): with 128-channel tiles only 8 - 32 CTAs have work and each
+    // walks its whole K loop alone (~30 us per launch, MMA-bound per CTA); 64-channel tiles put twice the SMs on it
+    if (NT == 128 && !main_fused && !short_fused &&
+        (int64_t)ceil_div(B * H * W, 128) * (Cout_pad / 128) * 2 <= conv_num_sms() / 2)
+        NT = 64;
 
     ConvParams p{};
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout_pad = Cout_pad; p.cout_store = cout_store;

@@ -241,7 +241,10 @@ struct FirTile {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+#ifndef DSEP_FIR_BLOCKS
+#define DSEP_FIR_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, DSEP_FIR_BLOCKS)   // 4 blocks of 46 KB per SM: the kernel is latency-bound (load -> sync -> stage -> sync)
 fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, const double* __restrict__ st,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
