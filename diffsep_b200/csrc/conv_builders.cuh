@@ -75,6 +75,15 @@ constexpr float kNegLog2e = -1.4426950408889634f;
 template <int NR>
 __device__ __forceinline__ void touch_rows(float4 (&v)[NR][2], const PatchPlan& d, const float* __restrict__ sc,
                                            const float* __restrict__ sh, float negzero) {
+    if (d.mode == 0 || (d.mode == 1 && sc == nullptr)) {
+        // raw operand (shortcut K-blocks, FIR-fed / im2col main operands): nothing to apply — ONE exact identity
+        // (x * 1 + (-0) == x; negzero is opaque to the compiler) per row is enough to make the warp wait for that row's
+        // load here, before the next burst goes out (the load writes all eight registers under one scoreboard)
+#pragma unroll
+        for (int u = 0; u < NR; ++u)
+            if ((d.inb >> u) & 1u) v[u][0].x = fmaf(v[u][0].x, 1.0f, negzero);
+        return;
+    }
     float k_sc[8], k_sh[8];
     if (d.mode != 0 && sc != nullptr) {
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + d.so));

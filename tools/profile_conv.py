@@ -28,7 +28,15 @@ reps = int(os.environ.get("DSEP_REPS", "5"))
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
 w = torch.randn(COUT, CIN, K, K, generator=g) / math.sqrt(CIN * K * K)
-cw = ConvWeight(w, torch.zeros(COUT), dev)
+short = int(os.environ.get("DSEP_SHORT", "0"))      # channels of a fused fp16 1x1 shortcut on a raw fp32 operand
+skw = {}
+if short:
+    w2 = torch.randn(COUT, short, 1, 1, generator=g) / math.sqrt(short)
+    cw = ConvWeight(w, torch.zeros(COUT), dev, shortcut=(w2, None))
+    xs = torch.randn(B, H, W, short, device=dev)
+    skw = dict(s0=xs, S0=short, Cin2=cw.cin2_pad, w2=cw.planes2)
+else:
+    cw = ConvWeight(w, torch.zeros(COUT), dev)
 x = torch.randn(B, H, W, CIN, device=dev)
 a = ops.Split.empty((B, H, W, CIN), dev)
 ops.split_f16(x, a)
@@ -43,7 +51,7 @@ if fused_in and passes == 2:      # experimental e4m3-correction mode (DSEP_LIB 
     run = lambda: ops.conv2d_fused(B, H, W, CIN, cw.planes8(), cw.cout_pad, K, out, COUT, x0=x, C0=CIN, sc=sc, sh=sh,
                                    act=1, bias=cw.bias, residual=res, scale=0.7071 if with_res else 1.0,
                                    acc_scale=cw.acc_scale, stats=stats, passes=2, corr_rel=cw.corr_rel,
-                                   a8_exp=cw.A8_EXP)
+                                   a8_exp=cw.A8_EXP, **skw)
 elif fused_in:
     run = lambda: ops.conv2d_fused(B, H, W, CIN, cw.planes, cw.cout_pad, K, out, COUT, x0=x, C0=CIN, sc=sc, sh=sh,
                                    act=1, bias=cw.bias, residual=res, scale=0.7071 if with_res else 1.0,
@@ -62,7 +70,7 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-fl = 2.0 * B * H * W * K * K * CIN * COUT
-print(f"conv {K}x{K} {CIN}->{COUT} {H}x{W} B={B} passes={passes} res={with_res} stats={with_stats} "
+fl = 2.0 * B * H * W * (K * K * CIN + short) * COUT
+print(f"conv {K}x{K} {CIN}->{COUT} {H}x{W} B={B} passes={passes} res={with_res} short={short} stats={with_stats} "
       f"fused_in={fused_in}: {ms:.3f} ms  "
       f"{fl / ms / 1e9:.1f} TFLOP/s algorithmic, {passes * fl / ms / 1e9:.1f} TFLOP/s issued", flush=True)
