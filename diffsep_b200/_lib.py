@@ -64,6 +64,8 @@ PROTOTYPES = {
     "dsep_sde_prior": [C.POINTER(SdeParams), _p, _i, _f, _p, _i, _p, _u64, _u64, _i, _i, _p, _p],
     "dsep_sde_corrector": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
     "dsep_sde_predictor": [C.POINTER(SdeParams), _p, _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _i, _p, _p, _p],
+    "dsep_sde_perturb": [C.POINTER(SdeParams), _p, _p, _p, _p, _u64, _u64, _i, _i, _p, _p, _p],
+    "dsep_score_loss": [C.POINTER(SdeParams), _p, _p, _p, _p, _i, _i, _p, _p],
     "dsep_sde_corrector_ald": [C.POINTER(SdeParams), _p, _p, _p, _p, _u64, _u64, _f, _i, _i, _p, _p, _p],
     "dsep_sde_corrector_langevin": [_p, _p, _p, _f, _i, _i, _p, _p, _p, _p],
     "dsep_sigma_mix": [_p, _i, _i, _i, _p, _p],

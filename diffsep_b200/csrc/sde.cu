@@ -402,6 +402,86 @@ static int launch_update_nc(const dsep_sde_params* p, const float* x, const floa
     return check_launch("sde_update_kernel");
 }
 
+// ------------------------------------------------------------------ training-side forward pieces
+// DiffSepModel.sample_prior with the default init_hack (pl_model.py:179-188, 243-247) and the arithmetic of
+// compute_score_loss around the network call (:418-424), on the marginal of the forward SDE (sdes.py:286-294,
+// 315-328 / 472-494, 515-532, 560-562):
+//   x_t = (A + e^{-lambda t} Pn) x0 + L(t) z,   L(t) = (s1 A + s2 Pn) [sigma_mix],    loss_b = mean_{c,t} ((L score) + z)^2
+// One pass each (the reference: marginal_prob's two matrix builds, two einsums / matmuls, randn_like, MSELoss).
+template <int VEC, int NC>
+__global__ void __launch_bounds__(256)
+sde_perturb_kernel(const dsep_sde_params p, const float* __restrict__ x0, const float* __restrict__ tvec,
+                   const float* __restrict__ sigma_mix, const float* __restrict__ noise, uint64_t seed, uint64_t offset,
+                   int T, float* __restrict__ x_t, float* __restrict__ z_out) {
+    const int b = blockIdx.y;
+    const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (t0 >= T) return;
+    const float t = tvec[b];
+    const SdeScalars sc = sde_scalars(p, t);
+    const float decay = expf(-t * p.d_lambda);
+    int64_t e[NC];
+    Vec<VEC> xv[NC], z[NC], o[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        e[c] = (static_cast<int64_t>(b) * NC + c) * T + t0;
+        xv[c] = ldv<VEC>(x0 + e[c]);
+        z[c] = noise_at<VEC>(noise, e[c], seed, offset);
+    }
+    Vec<VEC> sm;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sm.v[i] = 1.0f;
+    if (sigma_mix != nullptr) sm = ldv<VEC>(sigma_mix + static_cast<int64_t>(b) * T + t0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        float a[NC], m[NC], w[NC], l[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { a[c] = xv[c].v[i]; w[c] = z[c].v[i]; }
+        apply_std<NC>(1.0f, decay, a, m);                  // mean = xbar + e^{-lambda t} (x0 - xbar)
+        apply_std<NC>(sc.s1, sc.s2, w, l);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) o[c].v[i] = m[c] + l[c] * sm.v[i];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        stv<VEC>(x_t + e[c], o[c]);
+        if (z_out != nullptr) stv<VEC>(z_out + e[c], z[c]);
+    }
+}
+
+// loss[b] += sum over this block's samples of ((L score)[c] + z[c])^2 / (NC T)   (loss zeroed by the entry point)
+template <int NC>
+__global__ void __launch_bounds__(256)
+score_loss_kernel(const dsep_sde_params p, const float* __restrict__ score, const float* __restrict__ z,
+                  const float* __restrict__ tvec, const float* __restrict__ sigma_mix, int T,
+                  double* __restrict__ loss) {
+    const int b = blockIdx.y;
+    const SdeScalars sc = sde_scalars(p, tvec[b]);
+    double acc = 0.0;
+    for (int t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < T; t0 += gridDim.x * blockDim.x) {
+        float a[NC], l[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a[c] = score[(static_cast<int64_t>(b) * NC + c) * T + t0];
+        apply_std<NC>(sc.s1, sc.s2, a, l);
+        const float sg = sigma_mix != nullptr ? sigma_mix[static_cast<int64_t>(b) * T + t0] : 1.0f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float d = l[c] * sg + z[(static_cast<int64_t>(b) * NC + c) * T + t0];
+            acc += static_cast<double>(d) * d;
+        }
+    }
+    __shared__ double s_acc[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += s_acc[w];
+        atomicAdd(loss + b, tot / (static_cast<double>(NC) * T));
+    }
+}
+
+
 template <int MODE>
 static int launch_update(const dsep_sde_params* p, const float* x, const float* score, const float* mix,
                          const float* t, const float* sigma_mix, const float* noise, uint64_t seed,
@@ -462,6 +542,44 @@ extern "C" int dsep_sde_predictor(const dsep_sde_params* p, const float* x, cons
     DSEP_REQUIRE(dt > 0.f, "sde_predictor: dt must be positive");
     return launch_update<2>(p, x, score, nullptr, t, sigma_mix, noise, seed, offset, dt, probability_flow ? 1 : 0, 1, B,
                             T, x_out, x_mean, (cudaStream_t)stream);
+}
+
+extern "C" int dsep_sde_perturb(const dsep_sde_params* p, const float* x0, const float* t, const float* sigma_mix,
+                                const float* noise, uint64_t seed, uint64_t offset, int B, int T, float* x_t,
+                                float* z_out, dsep_stream_t stream) {
+    int rc = check_sde("sde_perturb", p, B, T);
+    if (rc) return rc;
+    DSEP_REQUIRE(x0 && t && x_t, "sde_perturb: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec = T % 4 == 0 && aligned(x0) && aligned(x_t) && (!sigma_mix || aligned(sigma_mix)) &&
+                     (!noise || aligned(noise)) && (!z_out || aligned(z_out));
+    const bool three = p->ndim == 3;
+    if (vec) {
+        dim3 grid(ceil_div(T / 4, 256), B);
+        if (three) sde_perturb_kernel<4, 3><<<grid, 256, 0, s>>>(*p, x0, t, sigma_mix, noise, seed, offset, T, x_t, z_out);
+        else sde_perturb_kernel<4, 2><<<grid, 256, 0, s>>>(*p, x0, t, sigma_mix, noise, seed, offset, T, x_t, z_out);
+    } else {
+        dim3 grid(ceil_div(T, 256), B);
+        if (three) sde_perturb_kernel<1, 3><<<grid, 256, 0, s>>>(*p, x0, t, sigma_mix, noise, seed, offset, T, x_t, z_out);
+        else sde_perturb_kernel<1, 2><<<grid, 256, 0, s>>>(*p, x0, t, sigma_mix, noise, seed, offset, T, x_t, z_out);
+    }
+    return check_launch("sde_perturb_kernel");
+}
+
+extern "C" int dsep_score_loss(const dsep_sde_params* p, const float* score, const float* z, const float* t,
+                               const float* sigma_mix, int B, int T, double* loss, dsep_stream_t stream) {
+    int rc = check_sde("score_loss", p, B, T);
+    if (rc) return rc;
+    DSEP_REQUIRE(score && z && t && loss, "score_loss: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(loss, 0, sizeof(double) * B, s) != cudaSuccess) return check_launch("score_loss: memset");
+    int gx = ceil_div(T, 256 * 8);
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, B);
+    if (p->ndim == 3) score_loss_kernel<3><<<grid, 256, 0, s>>>(*p, score, z, t, sigma_mix, T, loss);
+    else score_loss_kernel<2><<<grid, 256, 0, s>>>(*p, score, z, t, sigma_mix, T, loss);
+    return check_launch("score_loss_kernel");
 }
 
 extern "C" int dsep_sde_corrector_ald(const dsep_sde_params* p, const float* x, const float* score,

@@ -250,6 +250,20 @@ def sde_predictor(p, x, score, t, sigma_mix, noise, seed, offset, dt, B, T, x_ou
          ptr(x_mean), stream())
 
 
+def sde_perturb(p, x0, t, sigma_mix, noise, seed, offset, B, T, x_t, z_out=None):
+    call("dsep_sde_perturb", C.byref(p), ptr(_f32(x0, "x0")), ptr(_f32(t, "t")), ptr(sigma_mix),
+         ptr(_f32(noise, "noise")), seed, offset, B, T, ptr(x_t), ptr(z_out), stream())
+    return x_t
+
+
+def score_loss(p, score, z, t, sigma_mix, B, T, loss):
+    if loss.dtype != torch.float64:
+        raise ValueError("loss must be float64 [B]")
+    call("dsep_score_loss", C.byref(p), ptr(_f32(score, "score")), ptr(_f32(z, "z")), ptr(_f32(t, "t")),
+         ptr(sigma_mix), B, T, ptr(loss), stream())
+    return loss
+
+
 def sde_corrector_ald(p, x, score, t, noise, seed, offset, snr, B, T, x_out, x_mean):
     call("dsep_sde_corrector_ald", C.byref(p), ptr(_f32(x, "x")), ptr(_f32(score, "score")), ptr(_f32(t, "t")),
          ptr(_f32(noise, "noise")), seed, offset, snr, B, T, ptr(x_out), ptr(x_mean), stream())

@@ -143,6 +143,32 @@ class DiffSepModel(torch.nn.Module):
     def cached_mixture(self, mix):
         return self.score_model.cached_mixture(mix)
 
+    # ------------------------------------------------------------------ training-side forward pieces (no autograd)
+    def sample_time(self, x):
+        """uniform in [t_eps, t_max] (pl_model.py:166-171, the default ``time_sampling_strategy``)."""
+        return torch.empty(x.shape[0], device=x.device, dtype=torch.float32).uniform_(self.t_eps, self.t_max)
+
+    def sample_prior(self, mix, target, time=None):
+        """``(x_t, time, L, z)`` of the reference's ``sample_prior`` with the default ``init_hack = false``
+        (pl_model.py:179-188, 243-247): x_t = mean + L z on ``sde.marginal_prob(target, time, mix)``.  ``L`` is returned
+        as the pair (time, mix) it is a function of — ``compute_score_loss`` applies it inside its kernel instead of
+        materialising the [B,n,n(,T)] tensor."""
+        if getattr(self.config.model, "init_hack", False):
+            raise NotImplementedError("sample_prior: only the default init_hack = false is built")
+        time = self.sample_time(target) if time is None else time
+        x_t, z = self.sde.marginal_sample(target, time, mix)
+        return x_t, time, (time, mix), z
+
+    def compute_score_loss(self, mix, target, time=None, reduction="mean"):
+        """The score-matching loss of the reference's ``compute_score_loss`` (pl_model.py:411-424), FORWARD ONLY — a
+        validation metric on this inference path (its kernels have no backward): perturb (one kernel), score network,
+        ``MSE(L score, -z)`` (one kernel).  ``reduction``: "mean" (MSELoss's default, config/model/default.yaml:44-45) or
+        "none" (per sample, :421-422)."""
+        x_t, time, _, z = self.sample_prior(mix, target, time)
+        pred_score = self(x_t, time, mix)
+        loss = self.sde.score_loss(pred_score, z, time, mix)
+        return loss.mean() if reduction == "mean" else loss
+
     def prepare_times(self, ts):
         return self.score_model.prepare_times(ts)
 

@@ -108,6 +108,30 @@ class SDE:
     def reverse(self, score_fn, probability_flow=False):
         return RSDE(self, score_fn, probability_flow)
 
+    # ---- training-side forward pieces (forward only, no autograd)
+    def marginal_sample(self, x0, t, y):
+        """x_t ~ p_t(x | x0) = N(mean, L L^T) of ``marginal_prob`` (sdes.py:322-324 / 560-562), i.e. the
+        ``x_t = mean + mult_std(L, z)`` of ``DiffSepModel.sample_prior`` (pl_model.py:247), in one kernel: -> (x_t, z)."""
+        self._check(x0, y)
+        x0, t = x0.contiguous().float(), t.contiguous().float()
+        B, _, T = x0.shape
+        if t.shape != (B,):
+            raise ValueError(f"expected one time per batch entry, got {tuple(t.shape)}")
+        x_t, z_out = torch.empty_like(x0), torch.empty_like(x0)
+        z, seed, off = _noise.SOURCE.next(x0.shape, x0.device)
+        ops.sde_perturb(self._params(), x0, t, self._sigma_mix(y), z, seed, off, B, T, x_t, z_out)
+        return x_t, z_out
+
+    def score_loss(self, score, z, t, y):
+        """per-sample ``mean((mult_std(L, score) + z)^2)`` over (channel, time): the MSE of ``compute_score_loss``
+        (pl_model.py:418-424) with ``reduction="none"`` semantics; float32 [B]."""
+        self._check(score, y)
+        B, _, T = score.shape
+        loss = torch.empty(B, dtype=torch.float64, device=score.device)
+        ops.score_loss(self._params(), score.contiguous().float(), z.contiguous().float(), t.contiguous().float(),
+                       self._sigma_mix(y), B, T, loss)
+        return loss.float()
+
 
 class RSDE:
     """Reverse-time SDE handle (reference sdes.py:109-173), reduced to what predictors use."""

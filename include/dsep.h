@@ -288,6 +288,20 @@ int dsep_scale_output(const float* mix, const float* sep, int B, int nsrc, int T
 /* z ~ N(0,1), n elements, Philox4x32-10 keyed by (seed, offset). */
 int dsep_randn(float* z, int64_t n, uint64_t seed, uint64_t offset, dsep_stream_t stream);
 
+/* Training-side forward pieces (forward only, no gradients).
+ * dsep_sde_perturb: DiffSepModel.sample_prior with the default init_hack (pl_model.py:179-188, 243-247) on
+ * sde.marginal_prob (sdes/sdes.py:322-324 / 560-562): x_t = (A + e^{-lambda t} Pn) x0 + L(t) z with
+ * L = (sqrt(ev1) A + sqrt(ev2) Pn) [* sigma_mix (PriorMixSDE; [B,T] from dsep_sigma_mix, else NULL)].  x0, x_t: [B,ndim,T];
+ * t: [B]; noise: an injected [B,ndim,T] tensor or NULL for the Philox stream (seed, offset); z_out (nullable)
+ * receives the noise that was used (compute_score_loss needs it).
+ * dsep_score_loss: the MSE of compute_score_loss after the network call (pl_model.py:418-424):
+ * loss[b] = mean over (channel, time) of ((L(t) score) + z)^2, float64 [B] (its mean over b is MSELoss's default). */
+int dsep_sde_perturb(const dsep_sde_params* p, const float* x0, const float* t, const float* sigma_mix,
+                     const float* noise, uint64_t seed, uint64_t offset, int B, int T, float* x_t, float* z_out,
+                     dsep_stream_t stream);
+int dsep_score_loss(const dsep_sde_params* p, const float* score, const float* z, const float* t,
+                    const float* sigma_mix, int B, int T, double* loss, dsep_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,27 @@ def prior_sampling(p, mix, z):
     return mean + ev1.sqrt()[:, None, None] * wbar + ev2.sqrt()[:, None, None] * (w - wbar)
 
 
+def marginal_mean(p, x0, t):
+    """mean of p_t(x | x0) = (A + e^{-lambda t} Pn) x0; sdes.py:286-294 / 472-494."""
+    decay = torch.exp(-t * p.d_lambda)[:, None, None]
+    xbar = x0.mean(dim=1, keepdim=True)
+    return xbar + decay * (x0 - xbar)
+
+
+def sample_prior(p, mix, target, time, z):
+    """DiffSepModel.sample_prior with the default ``init_hack = false`` (pl_model.py:179-188, 243-247):
+    x_t = mean(target, t) + L(t) z with (mean, L) = sde.marginal_prob(target, t, mix) (sdes.py:322-324 / 560-562).
+    ``time`` and ``z`` are given (the reference draws them with uniform_ / randn_like)."""
+    return marginal_mean(p, target, time) + mult_L(p, time, z, mix)
+
+
+def score_loss(p, score, z, time, mix=None, reduction="mean"):
+    """DiffSepModel.compute_score_loss after the network call (pl_model.py:418-424): MSE between L(t) score and -z;
+    ``reduction="none"`` gives the per-sample mean over (channel, time) of :421-422."""
+    e = (mult_L(p, time, score, mix) + z) ** 2
+    return e.mean() if reduction == "mean" else e.mean(dim=(-2, -1))
+
+
 def diffusion(p, t, mix=None):
     """g(t) = sigma_min ratiosig^t sqrt(2 logsig) [* sigma_mix]; sdes.py:282-283 / 465-469."""
     g = p.sigma_min * p.ratiosig ** t * math.sqrt(2 * p.logsig)

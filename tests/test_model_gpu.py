@@ -598,3 +598,33 @@ def test_shape_cache_is_bounded():
         y = sm(xt, t, mix)
         assert y.shape == (1, 2, T) and bool(torch.isfinite(y).all())
     assert len(sm._bufs) <= sm.MAX_SHAPES and len(sm.backbone._plans) <= sm.MAX_SHAPES
+
+
+def test_compute_score_loss_forward_vs_oracle():
+    """DiffSepModel.compute_score_loss (forward only): perturb kernel + nf=64 score network + loss
+    kernel against the oracle's sample_prior / score_forward / score_loss on the same times and injected noise."""
+    import copy
+    from diffsep_b200 import sdes
+    from diffsep_b200.pl_model import DEFAULT_CONFIG, DiffSepModel
+    from oracle import score_ref as sr, sde_ref as sd, weights as ow
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg["model"]["score_model"]["backbone_args"]["nf"] = 64
+    model = DiffSepModel(cfg, score_state_dict=ow.make_score_model_state_dict(nf=64, seed=0))
+    params = ow.make_backbone_params(nf=64, seed=0)
+    B, T = 2, 4096
+    g = cases.gen(77)
+    target = torch.randn(B, 2, T, generator=g) * 0.2
+    mix = target.sum(dim=1, keepdim=True)
+    time = torch.tensor([0.2, 0.9])
+    z = torch.randn(B, 2, T, generator=g)
+    p = sd.MixSDEParams(N=30)
+    xt_w = sd.sample_prior(p, mix, target, time, z)
+    with torch.no_grad():
+        score_w = sr.score_forward(params, xt_w, time, mix)
+    want = sd.score_loss(p, score_w, z, time, mix, "none")
+    with sdes.injected_noise([z]):
+        got = model.compute_score_loss(mix.to(DEV), target.to(DEV), time=time.to(DEV), reduction="none")
+    torch.cuda.synchronize()
+    assert rel_l2(got.cpu(), want) < 1e-4
+    t2 = model.sample_time(target.to(DEV))
+    assert t2.shape == (B,) and float(t2.min()) >= model.t_eps and float(t2.max()) <= model.t_max

@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 import cases
-from conftest import ROOT, rel_l2
+from conftest import GOLDEN, ROOT, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -834,3 +834,32 @@ def test_conv_variants_cta_pair_mma_and_per_tap():
                             "test_conv2d_tc and not variants"], env=dict(os.environ, **env), capture_output=True,
                            text=True, timeout=600)
         assert r.returncode == 0, (env, r.stdout[-2000:])
+
+
+@pytest.mark.parametrize("name,prior,ndim", [("mix", False, 2), ("priormix", True, 2), ("priormix3", True, 3)])
+def test_training_forward_pieces_vs_reference_golden(name, prior, ndim):
+    """SURVEY section 8 f-4 (forward only): SDE.marginal_sample (dsep_sde_perturb: x_t = mean + L z of sample_prior,
+    pl_model.py:179-247) and SDE.score_loss (dsep_score_loss: MSE(L score, -z), :418-424) against outputs of the REAL
+    reference's marginal_prob / mult_std (tests/golden/training.npz), with injected noise; plus the in-kernel Philox
+    path (z_out reproduces the x_t it produced)."""
+    from diffsep_b200 import sdes
+    g = np.load(GOLDEN / "training.npz")
+    t = lambda k: torch.from_numpy(g[f"{name}_{k}"])
+    target = t("target").to(DEV)
+    mix = target.sum(dim=1, keepdim=True)
+    kw = dict(ndim=ndim, d_lambda=2.0, sigma_min=0.05, sigma_max=0.5, N=30)
+    sde = sdes.PriorMixSDE(**kw) if prior else sdes.MixSDE(**kw)
+    time = t("time").to(DEV)
+    with sdes.injected_noise([t("z")]):
+        x_t, z = sde.marginal_sample(target, time, mix)
+    torch.cuda.synchronize()
+    assert torch.equal(z.cpu(), t("z"))
+    assert rel_l2(x_t.cpu(), t("xt")) < 2e-6
+    loss = sde.score_loss(t("score").to(DEV), z, time, mix)
+    assert rel_l2(loss.cpu(), t("loss_none")) < 2e-6
+    assert abs(float(loss.mean()) - float(t("loss_mean"))) < 2e-6 * float(t("loss_mean"))
+    # Philox stream: the returned z is the noise that went into x_t
+    x2, z2 = sde.marginal_sample(target, time, mix)
+    with sdes.injected_noise([z2.cpu()]):
+        x3, _ = sde.marginal_sample(target, time, mix)
+    assert torch.equal(x2, x3) and abs(float(z2.mean())) < 0.05 and abs(float(z2.std()) - 1.0) < 0.05

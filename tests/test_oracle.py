@@ -193,3 +193,18 @@ def test_three_sources_and_true_mean_prior(golden, case):
                              denoise=True, true_mean=tm)
     assert nfe == cases.NDIM_N * (cs + 1) and out.shape == (cases.NDIM_B, ndim, cases.NDIM_T)
     assert rel_l2(out, g[name]) < 5e-6
+
+
+@pytest.mark.parametrize("name,prior,ndim", [("mix", False, 2), ("priormix", True, 2), ("priormix3", True, 3)])
+def test_training_forward_pieces_match_reference_golden(name, prior, ndim):
+    """oracle sample_prior / score_loss (pl_model.py:179-247, 411-424 on sde.marginal_prob / mult_std) vs outputs of the
+    REAL reference (tests/golden/make_golden_training.py)."""
+    g = np.load(GOLDEN / "training.npz")
+    p = sd.MixSDEParams(ndim=ndim, prior=prior)
+    t = lambda k: torch.from_numpy(g[f"{name}_{k}"])
+    target = t("target")
+    mix = target.sum(dim=1, keepdim=True)
+    assert rel_l2(sd.marginal_mean(p, target, t("time")), t("mean")) < 1e-6
+    assert rel_l2(sd.sample_prior(p, mix, target, t("time"), t("z")), t("xt")) < 1e-6
+    assert rel_l2(sd.score_loss(p, t("score"), t("z"), t("time"), mix, "none"), t("loss_none")) < 1e-6
+    assert abs(float(sd.score_loss(p, t("score"), t("z"), t("time"), mix)) - float(t("loss_mean"))) < 1e-6
