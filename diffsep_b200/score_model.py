@@ -23,7 +23,7 @@ import os
 import torch
 
 from . import ops
-from .backbone import NCSNppB200
+from .backbone import ConvWeight, NCSNppB200, cin_align
 from .ops import Split
 
 N_BINS = 256
@@ -94,6 +94,10 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self.backbone = None
         self.window = torch.hann_window(self.n_fft, dtype=torch.float32).to(self.dev)
         self.basis_fwd, self.basis_inv = _dft_bases(self.n_fft, self.dev)
+        # DFT-510 / inverse as a 1x1 "convolution" on the tensor core (three fp16 products, fp32-grade: the row
+        # matrix [M, 512] is the image [1, M/8, 8, 512]) instead of the fp32 CUDA-core GEMM, when M % 8 == 0
+        self._stft_tc = bool(int(os.environ.get("DSEP_STFT_TC", "1")))
+        self._basis_cw = {}
         self._bufs = {}
         self._mix_cache = None     # (data_ptr, B, T) of the mixture whose spectrogram is resident
         self._mix_cache_on = False
@@ -116,6 +120,18 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self._bufs = {}        # drops captured graphs that reference the old weights
         self._film_cache = {}
         return self
+
+    def _dft(self, src, which, dst, M):
+        """dst[M, LD] = src[M, LD] @ basis (``which``: "fwd" / "inv")."""
+        basis = self.basis_fwd if which == "fwd" else self.basis_inv
+        if not (self._stft_tc and M % 8 == 0 and M >= 128 and cin_align() == 64):
+            ops.sgemm(src, LD, basis, LD, dst, LD, M, LD, LD)
+            return
+        cw = self._basis_cw.get(which)
+        if cw is None:
+            cw = self._basis_cw[which] = ConvWeight(basis.t().contiguous().reshape(LD, LD, 1, 1), None, self.dev)
+        ops.conv2d_fused(1, M // 8, 8, LD, cw.planes, cw.cout_pad, 1, dst, LD, x0=src, C0=LD, act=0,
+                         acc_scale=cw.acc_scale, passes=3)
 
     # -------------------------------------------------------------- buffers per (B, T)
     MAX_SHAPES = 4   # distinct (batch, length) shapes kept resident (buffers, launch plan, CUDA graph)
@@ -217,7 +233,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
                 return self._replay(xt, time, bf, self._film_row())
         else:
             ops.stft_frames(mix, self.window, B, 1, T, Fr, bf["frames_mix"])
-            ops.sgemm(bf["frames_mix"], LD, self.basis_fwd, LD, bf["dft_mix"], LD, B * Fr, LD, LD)
+            self._dft(bf["frames_mix"], "fwd", bf["dft_mix"], B * Fr)
             ops.spec_pack(bf["dft_mix"], B, 1, Fr, Wp, ns, ns + 1, self.backbone.conv_in.cin_pad, self.spec_factor,
                           self.spec_abs_exponent,
                           bf["x_pyr"], bf["x_planes"])
@@ -229,7 +245,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         B, ns, T = xt.shape
         Fr, Wp = bf["Fr"], bf["Wp"]
         ops.stft_frames(xt, self.window, B, ns, T, Fr, bf["frames"])
-        ops.sgemm(bf["frames"], LD, self.basis_fwd, LD, bf["dft"], LD, B * ns * Fr, LD, LD)
+        self._dft(bf["frames"], "fwd", bf["dft"], B * ns * Fr)
         ops.spec_pack(bf["dft"], B, ns, Fr, Wp, 0, ns + 1, self.backbone.conv_in.cin_pad, self.spec_factor,
                       self.spec_abs_exponent,
                       bf["x_pyr"], bf["x_planes"])
@@ -238,7 +254,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         pyr = self.backbone(bf["x_planes"], bf["x_pyr"], time, uniform=film_row is not None)
         ops.out_head(pyr, B, Wp, self.ch_in, ns, Fr, time, self.backbone.out_w, self.backbone.out_b,
                      self.spec_factor, self.spec_abs_exponent, bf["spec_out"])
-        ops.sgemm(bf["spec_out"], LD, self.basis_inv, LD, bf["frames_out"], LD, B * ns * Fr, LD, LD)
+        self._dft(bf["spec_out"], "inv", bf["frames_out"], B * ns * Fr)
         out = torch.empty(B, ns, T, device=self.dev, dtype=torch.float32)
         ops.istft_ola(bf["frames_out"], self.window, B, ns, Fr, T, out)
         return out

@@ -628,3 +628,25 @@ def test_compute_score_loss_forward_vs_oracle():
     assert rel_l2(got.cpu(), want) < 1e-4
     t2 = model.sample_time(target.to(DEV))
     assert t2.shape == (B,) and float(t2.min()) >= model.t_eps and float(t2.max()) <= model.t_max
+
+
+def test_stft_gemms_on_the_tensor_core_match_the_fp32_gemm():
+    """ScoreModelNCSNpp._dft: the DFT-510 / inverse products as a 1x1 convolution with three fp16 tensor-core products
+    (fp32-grade) against the fp32 CUDA-core GEMM and a float64 product, forward and inverse, at the benchmark's row
+    count (B * ns * Fr = 64 * 251) and at a row count that falls back to the GEMM (M % 8 != 0)."""
+    from diffsep_b200 import ops
+    from diffsep_b200.score_model import ScoreModelNCSNpp, LD
+    sm = ScoreModelNCSNpp(num_sources=2, backbone_args=dict(nf=64))
+    g = cases.gen(5)
+    for M in (64 * 251, 2 * 251):
+        src = torch.randn(M, LD, generator=g).to(DEV)
+        src[:, 510:] = 0.0
+        for which, basis in (("fwd", sm.basis_fwd), ("inv", sm.basis_inv)):
+            want = (src.double() @ basis.double()).cpu()
+            ref = torch.empty(M, LD, device=DEV)
+            ops.sgemm(src, LD, basis, LD, ref, LD, M, LD, LD)
+            got = torch.full((M, LD), float("nan"), device=DEV)
+            sm._dft(src, which, got, M)
+            torch.cuda.synchronize()
+            assert rel_l2(ref.cpu(), want) < 1e-6
+            assert rel_l2(got.cpu(), want) < 2e-6, (M, which)
