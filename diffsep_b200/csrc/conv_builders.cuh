@@ -119,7 +119,7 @@ __device__ __forceinline__ void touch_rows(float4 (&v)[NR][2], const PatchPlan& 
 // the packed fp16 pairs (the host passes a8_exp = 0) and A_lo8 = e4m3(lo * a8_lo); else the fp16 lo plane.
 // SILU: 1 / 0 = known at compile time (no copy of the row in front of a run-time branch), -1 = the `silu` argument.
 template <bool E4M3, int SILU = -1>
-__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool inside, bool silu, uint32_t dst_hi,
+__device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, bool silu, uint32_t dst_hi,
                                               uint32_t dst_2, float a8_lo) {
     if (SILU >= 0) silu = SILU != 0;
     // rows outside the image arrive as zeros (load_rows) and come out as zeros: one straight-line body per row
@@ -159,7 +159,6 @@ __device__ __forceinline__ void convert_store(const float4 v0, const float4 v1, 
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[e]) : "f"(d1), "f"(d0));
         }
     }
-    (void)inside;
     sts128(dst_hi, hi[0], hi[1], hi[2], hi[3]);
     sts128(dst_2, lo[0], lo[1], lo[2], lo[3]);
 }
@@ -181,7 +180,7 @@ __device__ __forceinline__ void convert_rows_g(const float4 (&v)[NR][2], const P
         const uint32_t sw = ((jchunk ^ ((r0 + rbias + ((u * KROWS) & 7u)) & 7u)) << 4);
         const uint32_t off = base + u * KROWS * 128u + sw;
         if (MASKED && !((cur.smask >> u) & 1u)) continue;
-        convert_store<E4M3, SILU>(v[u][0], v[u][1], ((cur.inb >> u) & 1u) != 0, silu, off, off + plane_stride, a8_lo);
+        convert_store<E4M3, SILU>(v[u][0], v[u][1], silu, off, off + plane_stride, a8_lo);
     }
 }
 

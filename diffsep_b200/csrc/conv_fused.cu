@@ -246,9 +246,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         // ---------------------------------------------------------------------- patch builders
         asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         const int wtid = static_cast<int>(threadIdx.x) - 128;
-        const uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
-        const uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
-        const uint32_t a_ring = smem_u32(stage_base);
+        uint32_t jchunk = static_cast<uint32_t>(wtid & 7);
+        uint32_t r0 = static_cast<uint32_t>(wtid >> 3);
+        uint32_t a_ring = smem_u32(stage_base);
+        // opaque to ptxas: it otherwise recomputes all three from %tid / the shared-memory window per patch ROW
+        asm volatile("" : "+r"(jchunk), "+r"(r0), "+r"(a_ring));
         const bool skip = (p.debug & 2) != 0;
         const float a8_lo = FP8 ? p.a8_lo : 0.f;         // a8_hi == 1 (the dispatch sends other prescales elsewhere)
 
@@ -310,12 +312,18 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_cons
         const float negzero = -(p.acc_scale * 0.0f);
         auto wait_slot = [&]() { role_wait(&aempty[as_], aph ^ 1u); };
         auto build = [&](const float4 (&v)[6][2], const PatchPlan& cur) {
-            const uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
+            uint32_t slot = a_ring + static_cast<uint32_t>(as_) * Cfg::kAStage;
+            asm volatile("" : "+r"(slot));              // once per patch, not per row
             const bool halo3 = cur.krows == 30u;        // shortcut patches are never halo patches
             if (FP8) {
-                if (cur.second) convert_rows<false, false>(v, cur, slot, r0, jchunk, 0.f);
-                else if (halo3) convert_rows<true, true>(v, cur, slot, r0, jchunk, a8_lo);
-                else convert_rows<true, false>(v, cur, slot, r0, jchunk, a8_lo);
+                // SiLU known at compile time in the row bodies of the 2-unit mode (conv_builders.cuh)
+                constexpr uint32_t PS = kPatchPlane;
+                const bool silu = cur.mode == 2;
+                if (cur.second) convert_rows_g<false, 32, 4, false, 6, 0>(v, cur, slot, r0, jchunk, 0.f, PS, 0u);
+                else if (halo3 && silu) convert_rows_g<true, 30, 6, false, 6, 1>(v, cur, slot, r0, jchunk, a8_lo, PS, 0u);
+                else if (halo3) convert_rows_g<true, 30, 6, false, 6, 0>(v, cur, slot, r0, jchunk, a8_lo, PS, 0u);
+                else if (silu) convert_rows_g<true, 32, 4, false, 6, 1>(v, cur, slot, r0, jchunk, a8_lo, PS, 0u);
+                else convert_rows_g<true, 32, 4, false, 6, 0>(v, cur, slot, r0, jchunk, a8_lo, PS, 0u);
             } else {
                 if (halo3) convert_rows<false, true>(v, cur, slot, r0, jchunk, 0.f);
                 else convert_rows<false, false>(v, cur, slot, r0, jchunk, 0.f);
