@@ -46,6 +46,7 @@ PROTOTYPES = {
     "dsep_channel_stats": [_p, _i, _i, _i, _p, _p],
     "dsep_zero": [_p, _i64, _p],
     "dsep_gn_act_split": [_p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p, _p],
+    "dsep_gn_stats_act_split": [_p, _i, _p, _p, _i, _p, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p, _p, _i, _p],
     "dsep_fir_resample": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
     "dsep_fir_resample8": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _i, _p],
     "dsep_fir_resample_f32": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p],

@@ -382,6 +382,16 @@ class _Plan:
             self.steps.append(lambda: ops.channel_stats(t, C, B, P, st))
         return x.st
 
+    def _stats_or_defer(self, x: Act):
+        """-> (statistics slot, compute flag).  On small maps (at most 64 pixels per batch entry: the conv tiles there
+        span several batch entries, so producers leave no fused statistics) the consuming gn_act_split computes the
+        sums itself and writes them to the slot (dsep_gn_stats_act_split): no channel_stats launch."""
+        if x.st is None and x.H * x.W <= 64 and x.C % 64 == 0 and 256 % (x.C // 4) == 0 \
+                and int(os.environ.get("DSEP_STATS_INLINE", "1")):
+            x.st = self._slot(x.C)
+            return x.st, 1
+        return self._ensure_stats(x), 0
+
     def _fused_slot(self, H, W, C):
         return self._slot(C) if (C >= 64 and _tile_has_one_batch_entry(H, W)) else None
 
@@ -454,13 +464,19 @@ class _Plan:
         Cin, Cout, H, W = C0 + C1, rb["cout"], x.H, x.W
         assert Cin == rb["cin"], (Cin, rb["cin"])
         g0 = gn_groups(Cin)
-        st0 = self._ensure_stats(x)
-        st1 = self._ensure_stats(skip) if skip is not None else None
         x0, x1 = x.t, (skip.t if skip is not None else None)
         Ho, Wo = (H * 2, W * 2) if mode == 1 else ((H // 2, W // 2) if mode == 2 else (H, W))
         gam0, bet0 = rb["gn0"]
         gam1, bet1 = rb["gn1"]
         fused = self._fusable(Ho, Wo, C0, C1, Cout)
+        mask0 = 0
+        if not fused and mode == 0:      # small maps: the gn_act_split in front of Conv_0 takes the sums itself
+            st0, m0 = self._stats_or_defer(x)
+            st1, m1 = self._stats_or_defer(skip) if skip is not None else (None, 0)
+            mask0 = m0 | (m1 << 1)
+        else:
+            st0 = self._ensure_stats(x)
+            st1 = self._ensure_stats(skip) if skip is not None else None
         h = Act(ar.f32(B, Ho, Wo, Cout), Cout, Ho, Wo, self._fused_slot(Ho, Wo, Cout))
         out_slot = self._fused_slot(Ho, Wo, Cout) if want_stats else None
 
@@ -518,7 +534,7 @@ class _Plan:
         r = ar.split(B, Ho, Wo, Cin) if rb["has_shortcut"] else None
         if mode == 0:
             self.steps.append(lambda: ops.gn_act_split(x0, C0, st0, x1, C1, st1, B, H * W, g0, gam0, bet0, GN_EPS,
-                                                       1, a=a, r=r))
+                                                       1, a=a, r=r, compute_mask=mask0))
         else:
             assert x1 is None and r is not None
             self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
@@ -526,11 +542,11 @@ class _Plan:
         self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st)
         ar.release(a)
         g1 = gn_groups(Cout)
-        st_h = self._ensure_stats(h)
+        st_h, mh = self._stats_or_defer(h)
         a2 = ar.split(B, Ho, Wo, Cout)
         ht = h.t
         self.steps.append(lambda: ops.gn_act_split(ht, Cout, st_h, None, 0, None, B, Ho * Wo, g1, gam1, bet1,
-                                                   GN_EPS, 1, a=a2))
+                                                   GN_EPS, 1, a=a2, compute_mask=mh))
         # conv1 never reads h (only a2), so its buffer is reused for the block output
         out = Act(h.t, Cout, Ho, Wo, out_slot)
         if rb["has_shortcut"]:

@@ -170,17 +170,61 @@ __device__ __forceinline__ float4 affine_act(const float4 v, const float4 sc, co
 
 // ------------------------------------------------------- GN + act + split (+ raw split)
 // grid (chunks, B); each thread converts one channel-quad of one pixel per step, two steps in flight.
+// One block's per-channel (sum, sum of squares) of ITS batch entry's [P, Cs] slab -> st[b, c, 2] (float64): the small
+// maps (8x8, 4x4: 16 - 64 pixels) whose conv tiles span several batch entries get no fused statistics from their
+// producer, and a separate channel_stats launch per tensor was 32 launches of pure latency per evaluation.
+__device__ __forceinline__ void slab_stats(const float* __restrict__ xs, int Cs, int P, int b, double* __restrict__ st,
+                                           float* s_red /* [256 * 8] */) {
+    const int Qs = Cs >> 2, rows = 256 / Qs;                // host guarantees 256 % Qs == 0
+    const int q = threadIdx.x % Qs, r = threadIdx.x / Qs;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float4* base = reinterpret_cast<const float4*>(xs + static_cast<size_t>(b) * P * Cs) + q;
+    auto add = [&](const float4 v) {
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        a[4] = fmaf(v.x, v.x, a[4]); a[5] = fmaf(v.y, v.y, a[5]); a[6] = fmaf(v.z, v.z, a[6]); a[7] = fmaf(v.w, v.w, a[7]);
+    };
+    int p = r;
+    for (; p + 3 * rows < P; p += 4 * rows) {        // four loads in flight (the slab comes from L2)
+        const float4 v0 = __ldg(base + static_cast<size_t>(p) * Qs), v1 = __ldg(base + static_cast<size_t>(p + rows) * Qs);
+        const float4 v2 = __ldg(base + static_cast<size_t>(p + 2 * rows) * Qs);
+        const float4 v3 = __ldg(base + static_cast<size_t>(p + 3 * rows) * Qs);
+        add(v0); add(v1); add(v2); add(v3);
+    }
+    for (; p < P; p += rows) add(__ldg(base + static_cast<size_t>(p) * Qs));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[threadIdx.x * 8 + i] = a[i];
+    __syncthreads();
+    if (threadIdx.x < Qs) {
+        double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int rr = 0; rr < rows; ++rr)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] += static_cast<double>(s_red[(rr * Qs + threadIdx.x) * 8 + i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double* o = st + (static_cast<size_t>(b) * Cs + threadIdx.x * 4 + j) * 2;
+            o[0] = t[j];
+            o[1] = t[4 + j];
+        }
+    }
+    __syncthreads();      // the block reads these sums back (gn_tables): block-scope ordering of its own global writes
+}
+
 __global__ void __launch_bounds__(256)
-gn_act_split_kernel(const float* __restrict__ x0, int C0, const double* __restrict__ st0,
-                    const float* __restrict__ x1, int C1, const double* __restrict__ st1, int P, int groups,
+gn_act_split_kernel(const float* __restrict__ x0, int C0, double* __restrict__ st0,
+                    const float* __restrict__ x1, int C1, double* __restrict__ st1, int P, int groups,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act,
                     f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
-                    f16x4* __restrict__ r_lo, int pix_per_block) {
-    extern __shared__ float s_tab[];   // sc[Ct] | sh[Ct] | mean[64] | rstd[64]
+                    f16x4* __restrict__ r_lo, int pix_per_block, int compute_mask) {
+    extern __shared__ float s_tab[];   // sc[Ct] | sh[Ct] | mean[64] | rstd[64]  (compute_mask: + [256 * 8] scratch)
     const int Ct = C0 + C1, Q = Ct >> 2;
     float* s_sc = s_tab;
     float* s_sh = s_tab + Ct;
     const int b = blockIdx.y;
+    if (compute_mask) {       // one block per batch entry (grid.x == 1)
+        float* s_red = s_tab + 2 * Ct + 128;
+        if (compute_mask & 1) slab_stats(x0, C0, P, b, st0, s_red);
+        if (compute_mask & 2) slab_stats(x1, C1, P, b, st1, s_red);
+    }
     gn_tables(st0, C0, st1, C1, b, groups, (double)P, gamma, beta, eps, s_sc, s_sh, s_tab + 2 * Ct,
               s_tab + 2 * Ct + 64);
     const int64_t e_begin = (int64_t)blockIdx.x * pix_per_block * Q;
@@ -558,10 +602,9 @@ extern "C" int dsep_gn_tables(const double* st0, int C0, const double* st1, int 
     return check_launch("gn_tables_kernel");
 }
 
-extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x1, int C1,
-                                 const double* st1, int B, int P, int groups, const float* gamma,
-                                 const float* beta, float eps, int act, void* a_hi, void* a_lo, void* r_hi,
-                                 void* r_lo, dsep_stream_t stream) {
+static int gn_act_split_impl(const float* x0, int C0, double* st0, const float* x1, int C1, double* st1, int B, int P,
+                             int groups, const float* gamma, const float* beta, float eps, int act, void* a_hi,
+                             void* a_lo, void* r_hi, void* r_lo, int compute_mask, dsep_stream_t stream) {
     DSEP_REQUIRE(x0 && (C1 == 0 || x1), "gn_act_split: null input");
     DSEP_REQUIRE((a_hi && a_lo) || (r_hi && r_lo), "gn_act_split: no output requested");
     DSEP_REQUIRE(st0 == nullptr || (gamma && beta && (C1 == 0 || st1)),
@@ -571,13 +614,42 @@ extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, con
     if (st0 == nullptr) groups = 1;
     int rc = check_gn_shape("gn_act_split", C0, C1, groups);
     if (rc) return rc;
-    const int ppb = pix_per_block_for(P, B);
+    int ppb = pix_per_block_for(P, B);
+    size_t smem = sizeof(float) * (2 * (C0 + C1) + 128);
+    if (compute_mask) {
+        DSEP_REQUIRE((compute_mask & ~3) == 0 && st0 && (!(compute_mask & 2) || (C1 > 0 && st1)),
+                     "gn_stats_act_split: bad compute mask %d", compute_mask);
+        DSEP_REQUIRE(P <= 1024 && (!(compute_mask & 1) || (C0 <= 1024 && 256 % (C0 / 4) == 0)) &&
+                         (!(compute_mask & 2) || (C1 <= 1024 && 256 % (C1 / 4) == 0)),
+                     "gn_stats_act_split: in-kernel statistics are for small maps (P <= 1024) and channel counts "
+                     "whose quads divide 256 (got P=%d, C0=%d, C1=%d)", P, C0, C1);
+        ppb = P;                                  // one block per batch entry
+        smem += sizeof(float) * 256 * 8;
+    }
     dim3 grid(ceil_div(P, ppb), B);
-    const size_t smem = sizeof(float) * (2 * (C0 + C1) + 128);
     gn_act_split_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
         x0, C0, st0, x1, C1, st1, P, groups, gamma, beta, eps, act, (f16x4*)a_hi, (f16x4*)a_lo, (f16x4*)r_hi,
-        (f16x4*)r_lo, ppb);
+        (f16x4*)r_lo, ppb, compute_mask);
     return check_launch("gn_act_split_kernel");
+}
+
+extern "C" int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x1, int C1,
+                                 const double* st1, int B, int P, int groups, const float* gamma,
+                                 const float* beta, float eps, int act, void* a_hi, void* a_lo, void* r_hi,
+                                 void* r_lo, dsep_stream_t stream) {
+    return gn_act_split_impl(x0, C0, const_cast<double*>(st0), x1, C1, const_cast<double*>(st1), B, P, groups, gamma,
+                             beta, eps, act, a_hi, a_lo, r_hi, r_lo, 0, stream);
+}
+
+// Same, computing the per-channel sums of x0 (compute_mask & 1) and / or x1 (& 2) in the kernel first and WRITING them
+// to st0 / st1 (later consumers of the tensor's statistics read them from there).
+extern "C" int dsep_gn_stats_act_split(const float* x0, int C0, double* st0, const float* x1, int C1, double* st1,
+                                       int B, int P, int groups, const float* gamma, const float* beta, float eps,
+                                       int act, void* a_hi, void* a_lo, void* r_hi, void* r_lo, int compute_mask,
+                                       dsep_stream_t stream) {
+    DSEP_REQUIRE(compute_mask != 0, "gn_stats_act_split: nothing to compute (use dsep_gn_act_split)");
+    return gn_act_split_impl(x0, C0, st0, x1, C1, st1, B, P, groups, gamma, beta, eps, act, a_hi, a_lo, r_hi, r_lo,
+                             compute_mask, stream);
 }
 
 template <int MODE>

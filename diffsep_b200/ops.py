@@ -143,7 +143,15 @@ def zero(t):
     return t
 
 
-def gn_act_split(x0, C0, st0, x1, C1, st1, B, P, groups, gamma, beta, eps, act, a: Split = None, r: Split = None):
+def gn_act_split(x0, C0, st0, x1, C1, st1, B, P, groups, gamma, beta, eps, act, a: Split = None, r: Split = None,
+                 compute_mask=0):
+    """compute_mask (small maps): bit 0 / 1 = compute the per-channel sums of x0 / x1 in the kernel and write them to
+    st0 / st1 first (dsep_gn_stats_act_split) instead of reading them."""
+    if compute_mask:
+        call("dsep_gn_stats_act_split", ptr(x0), C0, ptr(st0), ptr(x1), C1, ptr(st1), B, P, groups, ptr(gamma),
+             ptr(beta), eps, act, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
+             ptr(r.lo) if r else None, compute_mask, stream())
+        return
     call("dsep_gn_act_split", ptr(x0), C0, ptr(st0), ptr(x1), C1, ptr(st1), B, P, groups, ptr(gamma), ptr(beta),
          eps, act, ptr(a.hi) if a else None, ptr(a.lo) if a else None, ptr(r.hi) if r else None,
          ptr(r.lo) if r else None, stream())

@@ -146,6 +146,13 @@ int dsep_gn_act_split(const float* x0, int C0, const double* st0, const float* x
                       const double* st1, int B, int P, int groups, const float* gamma, const float* beta,
                       float eps, int act, void* a_hi, void* a_lo, void* r_hi, void* r_lo,
                       dsep_stream_t stream);
+/* The same pass for SMALL maps (P <= 1024 pixels per batch entry: the 8x8 / 4x4 levels, whose conv tiles span several
+ * batch entries and therefore get no fused statistics from their producer): one block per batch entry first computes
+ * the per-channel (sum, sum of squares) of x0 (compute_mask & 1) and / or x1 (& 2) and WRITES them to st0 / st1
+ * ([B,C,2] float64, as dsep_channel_stats would), then proceeds as dsep_gn_act_split.  Saves one launch per tensor. */
+int dsep_gn_stats_act_split(const float* x0, int C0, double* st0, const float* x1, int C1, double* st1, int B, int P,
+                            int groups, const float* gamma, const float* beta, float eps, int act, void* a_hi,
+                            void* a_lo, void* r_hi, void* r_lo, int compute_mask, dsep_stream_t stream);
 /* 2x FIR resampling with taps [1,3,3,1] of an fp32 [B,H,W,C] tensor (mode 1: up, 2: down).
  * Outputs (each nullable pair): a = FIR(act(GN(x))) split, r = FIR(x) split, y = FIR(x) fp32.
  * st/gamma/beta NULL => no GroupNorm branch.

@@ -581,6 +581,45 @@ def test_groupnorm_silu_split(shape, act):
     assert rel_l2(nchw(r.hi.float() + r.lo.float()), xcat) < 1e-6
 
 
+@pytest.mark.parametrize("shape", [(3, 8, 8, 256, 0), (2, 4, 4, 256, 256), (5, 8, 8, 128, 256), (1, 4, 4, 512, 0)])
+def test_gn_act_split_with_in_kernel_statistics(shape):
+    """dsep_gn_stats_act_split (the 8x8 / 4x4 levels): the per-channel sums of the (concatenated) input computed by the
+    same launch equal dsep_channel_stats', are left in the statistics slots for later consumers, and the planes are
+    bit-identical to the two-launch form; a mask that covers only one half of a concat reads the other half's sums."""
+    ops = _ops()
+    B, H, W, C0, C1 = shape
+    g = cases.gen(sum(shape) + 23)
+    x0 = torch.randn(B, C0, H, W, generator=g) * 1.7 + 0.3
+    x1 = torch.randn(B, C1, H, W, generator=g) * 0.6 - 0.2 if C1 else None
+    Ct = C0 + C1
+    gamma = (1 + 0.1 * torch.randn(Ct, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(Ct, generator=g)).to(DEV)
+    groups = 32
+    d0, d1 = cl(x0), (cl(x1) if C1 else None)
+    st0 = torch.empty(B, C0, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d0, C0, B, H * W, st0)
+    st1 = None
+    if C1:
+        st1 = torch.empty(B, C1, 2, dtype=torch.float64, device=DEV)
+        ops.channel_stats(d1, C1, B, H * W, st1)
+    a_ref, r_ref = ops.Split.empty((B, H, W, Ct), DEV), ops.Split.empty((B, H, W, Ct), DEV)
+    ops.gn_act_split(d0, C0, st0, d1, C1, st1, B, H * W, groups, gamma, beta, 1e-6, 1, a=a_ref, r=r_ref)
+    for mask in ([1, 3, 2] if C1 else [1]):
+        t0 = st0.clone() if not (mask & 1) else torch.full_like(st0, float("nan"))
+        t1 = None if not C1 else (st1.clone() if not (mask & 2) else torch.full_like(st1, float("nan")))
+        a, r = ops.Split.empty((B, H, W, Ct), DEV), ops.Split.empty((B, H, W, Ct), DEV)
+        ops.gn_act_split(d0, C0, t0, d1, C1, t1, B, H * W, groups, gamma, beta, 1e-6, 1, a=a, r=r, compute_mask=mask)
+        torch.cuda.synchronize()
+        assert rel_l2(t0.cpu(), st0.cpu()) < 1e-6 and (not C1 or rel_l2(t1.cpu(), st1.cpu()) < 1e-6)
+        assert rel_l2(t0[..., 0].cpu(), x0.double().sum(dim=(2, 3))) < 1e-6
+        assert rel_l2(a.hi.float() + a.lo.float(), a_ref.hi.float() + a_ref.lo.float()) < 1e-6, mask
+        assert torch.equal(r.hi, r_ref.hi) and torch.equal(r.lo, r_ref.lo)
+    with pytest.raises(ValueError):      # large maps keep the separate statistics pass
+        ops.gn_act_split(torch.zeros(1, 64, 64, 64, device=DEV), 64, torch.zeros(1, 64, 2, dtype=torch.float64, device=DEV),
+                         None, 0, None, 1, 4096, 16, gamma[:64], beta[:64], 1e-6, 1,
+                         a=ops.Split.empty((1, 64, 64, 64), DEV), compute_mask=1)
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_fir_resample_matches_reference_golden(golden, mode):
     """FIR x2 up / down vs the golden produced by the reference's upsample_2d / downsample_2d
