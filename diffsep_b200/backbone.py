@@ -499,7 +499,6 @@ class _Plan:
             ar.release(h.t)
             return out
 
-        a = ar.split(B, Ho, Wo, Cin)
         if fused:
             # up / down block on a large map: one FIR pass writes a = FIR(SiLU(GN0(x))) as planes for
             # Conv_0 and FIR(x) in fp32; Conv_1 applies GN1+SiLU to h and splits FIR(x) for the
@@ -517,11 +516,12 @@ class _Plan:
                                  film=rb["film_off"], stats=h.st)
                 ar.release(af)
             else:
+                a = ar.split(B, Ho, Wo, Cin)
                 a8 = ConvWeight.A8_EXP if e4 else None
                 self.steps.append(lambda: ops.fir_resample(x0, B, H, W, Cin, mode, g0, st0, gam0, bet0, GN_EPS,
                                                            a=a, y=xr, a8_exp=a8))
                 self._conv(a, Ho, Wo, Cin, rb["conv0"], h.t, Cout, film=rb["film_off"], stats=h.st, e4m3=e4)
-            ar.release(a)
+                ar.release(a)
             st_h = self._ensure_stats(h)
             sc1, sh1 = self._tables(st_h, Cout, None, 0, Ho * Wo, gam1, bet1)
             out = Act(ar.f32(B, Ho, Wo, Cout), Cout, Ho, Wo, out_slot)
@@ -531,6 +531,7 @@ class _Plan:
             ar.release(xr)
             ar.release(h.t)
             return out
+        a = ar.split(B, Ho, Wo, Cin)
         r = ar.split(B, Ho, Wo, Cin) if rb["has_shortcut"] else None
         if mode == 0:
             self.steps.append(lambda: ops.gn_act_split(x0, C0, st0, x1, C1, st1, B, H * W, g0, gam0, bet0, GN_EPS,
