@@ -49,6 +49,9 @@ struct WideCfg {
 static_assert(WideCfg::kSmemBytes <= 232448, "conv_wide: shared memory");
 static_assert(340 * 128 <= WideCfg::kPlaneBytes, "conv_wide: patch plane");
 
+// CS: the output's channel count when it is 128 or 256 (the pixel stride of the epilogue's per-lane loads / stores
+// becomes an immediate: their address arithmetic was ~40 % of the epilogue's instructions), 0 = run-time value.
+template <int CS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1)
 conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                  const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
@@ -378,7 +381,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
         const int wq = warp & 3;               // TMEM lane quarter == warp_id % 4: channels n0 + 32 wq + lane
         const float as2 = p.acc_scale * p.scale;
         const bool store = !(p.debug & 4);
-        const uint32_t C = static_cast<uint32_t>(p.cout_store);
+        const uint32_t C = CS ? static_cast<uint32_t>(CS) : static_cast<uint32_t>(p.cout_store);
         int run_b = -1, run_n0 = -1;
         float s1 = 0.f, s2 = 0.f;              // running GroupNorm sums of this lane's channel over one batch entry
         float bz = 0.f;                        // (bias + FiLM) * scale of this lane's channel
@@ -472,18 +475,25 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
     if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-int launch_conv_wide(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
+template <int CS>
+static int launch_wide(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
     constexpr int kSmem = WideCfg::kSmemBytes;
     static PerDeviceAttr attr;
-    const cudaError_t attr_err = set_max_smem_once(attr, conv_wide_kernel, kSmem);
+    const cudaError_t attr_err = set_max_smem_once(attr, conv_wide_kernel<CS>, kSmem);
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_wide_kernel): %s", cudaGetErrorString(attr_err));
         return DSEP_ERR_CUDA;
     }
     const int max_clusters = conv_num_sms() / 2;
     const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
-    conv_wide_kernel<<<grid, kWThreads, kSmem, stream>>>(m.w_hi, m.w_lo, m.w2_hi, m.w2_lo, p);
+    conv_wide_kernel<CS><<<grid, kWThreads, kSmem, stream>>>(m.w_hi, m.w_lo, m.w2_hi, m.w2_lo, p);
     return check_launch("conv_wide_kernel");
+}
+
+int launch_conv_wide(const ConvMaps& m, const ConvParams& p, cudaStream_t stream) {
+    if (p.cout_store == 128) return launch_wide<128>(m, p, stream);
+    if (p.cout_store == 256) return launch_wide<256>(m, p, stream);
+    return launch_wide<0>(m, p, stream);
 }
 
 }  // namespace dsep
