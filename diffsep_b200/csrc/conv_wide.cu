@@ -395,6 +395,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
             }
         };
         float res[2][32];          // residual values of this lane's channel, double-buffered over the 32-pixel chunks
+        const float negzero_e = -(p.acc_scale * 0.0f);      // opaque -0: x * 1 + (-0) == x exactly
         int it = 0;
         for (int item = cluster_id; item < p.total_items; item += num_clusters, ++it) {
             const int as = it & 1;
@@ -439,9 +440,9 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
             for (int c = 0; c < 8; ++c) {
                 if (res0 != nullptr) {
                     // touch the current buffer BEFORE the next burst is issued (all these loads share one scoreboard:
-                    // a consumer of the current chunk would otherwise wait for the next chunk's loads as well)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) res[c & 1][j] *= p.scale;
+                    // a consumer of the current chunk would otherwise wait for the next chunk's loads as well); one
+                    // dependent instruction on its newest load is enough, the scale rides in the FMA below
+                    res[c & 1][31] = fmaf(res[c & 1][31], 1.0f, negzero_e);   // exact identity on the NEWEST load
                     __syncwarp();
                     if (c + 1 < 8) load_res(c + 1, res[(c + 1) & 1]);
                 }
@@ -458,7 +459,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float a = fmaf(__uint_as_float(v[j]), as2, bz);
-                        if (res0 != nullptr) a += res[c & 1][j];
+                        if (res0 != nullptr) a = fmaf(res[c & 1][j], p.scale, a);
                         if (store) orow[static_cast<size_t>(j >> 3) * d_row + (j & 7) * C] = a;
                         s1 += a;
                         s2 = fmaf(a, a, s2);
