@@ -96,8 +96,11 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self.basis_fwd, self.basis_inv = _dft_bases(self.n_fft, self.dev)
         # DFT-510 / inverse as a 1x1 "convolution" on the tensor core (three fp16 products, fp32-grade: the row
         # matrix [M, 512] is the image [1, M/8, 8, 512]) instead of the fp32 CUDA-core GEMM, when M % 8 == 0
-        self._stft_tc = bool(int(os.environ.get("DSEP_STFT_TC", "1")))
+        self._stft_tc = bool(int(os.environ.get("DSEP_STFT_TC", "1"))) and cin_align() == 64
         self._basis_cw = {}
+        if self._stft_tc:      # built now (allocations + a host sync), never inside a CUDA-graph capture
+            for which, basis in (("fwd", self.basis_fwd), ("inv", self.basis_inv)):
+                self._basis_cw[which] = ConvWeight(basis.t().contiguous().reshape(LD, LD, 1, 1), None, self.dev)
         self._bufs = {}
         self._mix_cache = None     # (data_ptr, B, T) of the mixture whose spectrogram is resident
         self._mix_cache_on = False
@@ -124,12 +127,10 @@ class ScoreModelNCSNpp(torch.nn.Module):
     def _dft(self, src, which, dst, M):
         """dst[M, LD] = src[M, LD] @ basis (``which``: "fwd" / "inv")."""
         basis = self.basis_fwd if which == "fwd" else self.basis_inv
-        if not (self._stft_tc and M % 8 == 0 and M >= 128 and cin_align() == 64):
+        if not (self._stft_tc and M % 8 == 0 and M >= 128):
             ops.sgemm(src, LD, basis, LD, dst, LD, M, LD, LD)
             return
-        cw = self._basis_cw.get(which)
-        if cw is None:
-            cw = self._basis_cw[which] = ConvWeight(basis.t().contiguous().reshape(LD, LD, 1, 1), None, self.dev)
+        cw = self._basis_cw[which]
         ops.conv2d_fused(1, M // 8, 8, LD, cw.planes, cw.cout_pad, 1, dst, LD, x0=src, C0=LD, act=0,
                          acc_scale=cw.acc_scale, passes=3)
 
