@@ -293,7 +293,7 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 f16x4* __restrict__ a_hi, f16x4* __restrict__ a_lo, f16x4* __restrict__ r_hi,
                 f16x4* __restrict__ r_lo, float4* __restrict__ y, float4* __restrict__ af, int tiles_w, int tiles_h,
-                float a8_hi, float a8_lo) {
+                float a8_hi, float a8_lo, int kt) {
     using FT = FirTile<MODE>;
     extern __shared__ __align__(16) float s_fir[];
     float4* s_act = reinterpret_cast<float4*>(s_fir);                  // [IH*IW][8 quads]
@@ -301,10 +301,15 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
     __shared__ float s_sc[32], s_sh[32];
     const int Ho = MODE == 1 ? H * 2 : H / 2, Wo = MODE == 1 ? W * 2 : W / 2;
     const int chunk = blockIdx.y, b = blockIdx.z;
-    const int tw_i = blockIdx.x % tiles_w, th_i = blockIdx.x / tiles_w;
-    const int oh0 = th_i * FT::OH, ow0 = tw_i * FT::OW;
+    // a block walks kt consecutive tiles of one tile row: the next tile's patch loads are in flight while the current
+    // tile is computed out of shared memory (one tile per block spent most of its life in load -> sync -> stage ->
+    // sync), and the GroupNorm scale / shift of the chunk is computed once per block
+    const int groups_w = (tiles_w + kt - 1) / kt;
+    const int th_i = blockIdx.x / groups_w;
+    const int tw_begin = (blockIdx.x % groups_w) * kt;
+    const int tw_end = min(tiles_w, tw_begin + kt);
+    const int oh0 = th_i * FT::OH;
     const int ih0 = MODE == 1 ? oh0 / 2 - 1 : oh0 * 2 - 1;
-    const int iw0 = MODE == 1 ? ow0 / 2 - 1 : ow0 * 2 - 1;
     const int c0 = chunk * 32;
     const bool want_act = a_hi != nullptr || af != nullptr;     // the GroupNorm + SiLU branch (planes and / or fp32)
     const bool xf = st != nullptr && want_act;
@@ -314,17 +319,22 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
     constexpr int NI = FT::IH * FT::IW * 8;
     constexpr int PER = (NI + 255) / 256;
     float4 raw[PER];
+    auto load_tile = [&](int tw_i) {
+        const int ow0 = tw_i * FT::OW;
+        const int iw0 = MODE == 1 ? ow0 / 2 - 1 : ow0 * 2 - 1;
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = threadIdx.x + k * 256;
-        raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < NI) {
-            const int q = i & 7, pix = i >> 3;
-            const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-                raw[k] = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + ih) * W + iw) * C + c0 + q * 4));
+        for (int k = 0; k < PER; ++k) {
+            const int i = threadIdx.x + k * 256;
+            raw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < NI) {
+                const int q = i & 7, pix = i >> 3;
+                const int ih = ih0 + pix / FT::IW, iw = iw0 + pix % FT::IW;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    raw[k] = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * H + ih) * W + iw) * C + c0 + q * 4));
+            }
         }
-    }
+    };
+    load_tile(tw_begin);
     if (threadIdx.x < 32) {
         float sc = 1.0f, sh = 0.0f;
         if (xf) {
@@ -344,6 +354,10 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
         s_sh[threadIdx.x] = sh;
     }
     __syncthreads();
+    const int Q = C >> 2;
+    for (int tw_i = tw_begin; tw_i < tw_end; ++tw_i) {
+    const int ow0 = tw_i * FT::OW;
+    const int iw0 = MODE == 1 ? ow0 / 2 - 1 : ow0 * 2 - 1;
     // stage the patch: out-of-image pixels are zero AFTER the activation (the FIR pads its input)
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
@@ -361,7 +375,7 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
         }
     }
     __syncthreads();
-    const int Q = C >> 2;
+    if (tw_i + 1 < tw_end) load_tile(tw_i + 1);        // in flight while this tile is computed
     for (int i = threadIdx.x; i < FT::OH * FT::OW * 8; i += blockDim.x) {
         const int q = i & 7, opix = i >> 3;
         const int oy = opix / FT::OW, ox = opix % FT::OW;
@@ -428,6 +442,8 @@ fir_tile_kernel(const float* __restrict__ x, int H, int W, int C, int groups, co
         if (r_hi != nullptr) { split4(acc_r, h, l); r_hi[o] = h; r_lo[o] = l; }
         if (y != nullptr) y[o] = acc_r;
         if (af != nullptr) af[o] = acc_a;
+    }
+    __syncthreads();       // every thread is done with this tile's shared-memory patch before the next one is staged
     }
 }
 
@@ -665,10 +681,14 @@ static int launch_fir_tile(const float* x, int B, int H, int W, int C, int group
     }
     const int Ho = MODE == 1 ? H * 2 : H / 2, Wo = MODE == 1 ? W * 2 : W / 2;
     const int tiles_w = ceil_div(Wo, FT::OW), tiles_h = ceil_div(Ho, FT::OH);
-    dim3 grid(tiles_w * tiles_h, C / 32, B);
+    // tiles per block along w: enough blocks to fill the GPU a few times over, at most 8 tiles each
+    static const int kt_env = getenv("DSEP_FIR_KT") ? atoi(getenv("DSEP_FIR_KT")) : 0;
+    int kt = kt_env > 0 ? kt_env : 4;
+    while (kt > 1 && (int64_t)tiles_h * ceil_div(tiles_w, kt) * (C / 32) * B < 148 * 8) kt >>= 1;
+    dim3 grid(tiles_h * ceil_div(tiles_w, kt), C / 32, B);
     fir_tile_kernel<MODE><<<grid, 256, FT::kSmemBytes, s>>>(x, H, W, C, groups, st, gamma, beta, eps, (f16x4*)a_hi,
                                                             (f16x4*)a_lo, (f16x4*)r_hi, (f16x4*)r_lo, (float4*)y,
-                                                            (float4*)af, tiles_w, tiles_h, a8_hi, a8_lo);
+                                                            (float4*)af, tiles_w, tiles_h, a8_hi, a8_lo, kt);
     return check_launch("fir_tile_kernel");
 }
 
