@@ -31,6 +31,8 @@ NUM_RES_BLOCKS = 2                # :51
 ATTN_RESOLUTIONS = (16,)          # :52
 GN_EPS = 1e-6                     # layerspp.py:264-266
 INV_SQRT2 = 1.0 / math.sqrt(2.0)
+# output-pyramid convs (C -> 6) on maps of at least this many pixels run as 1x1 conv + tap gather (0: never)
+PYR_TAPS_MIN_PIXELS = int(os.environ.get("DSEP_PYR_TAPS_MIN", str(64 * 64))) or (1 << 62)
 
 
 def _round_up(v, m):
@@ -59,13 +61,14 @@ class ConvWeight:
     ``shortcut`` (a 1x1 ConvWeight source: weight, bias) is folded in as the fused second operand of
     ``dsep_conv2d_tc``: both weights share one power-of-two pre-scale and the biases are summed."""
 
-    def __init__(self, w_oihw, bias, device, shortcut=None):
+    def __init__(self, w_oihw, bias, device, shortcut=None, cout_pad=None):
         w = w_oihw.detach().to(device=device, dtype=torch.float32)
         cout, cin, kh, kw = w.shape
         assert kh == kw and kh in (1, 3)
         self.ksize, self.cout, self.cin = kh, cout, cin
         self.cin_pad = _round_up(cin, cin_align())
-        self.cout_pad = 16 if cout <= 16 else _round_up(cout, 64)
+        self.cout_pad = (16 if cout <= 16 else _round_up(cout, 64)) if cout_pad is None else cout_pad
+        assert self.cout_pad >= cout
         wt = torch.zeros(kh * kw, self.cout_pad, self.cin_pad, device=device, dtype=torch.float32)
         wt[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
         amax = float(wt.abs().max())
@@ -286,7 +289,14 @@ class NCSNppB200:
             if res in ATTN_RESOLUTIONS:
                 level["attn"] = attn(m); m += 1
             level["pyr_gn"] = (f32(mod(m, "weight")), f32(mod(m, "bias"))); m += 1
-            level["pyr_conv"] = ConvWeight(P[mod(m, "weight")], P[mod(m, "bias")], dev); m += 1
+            level["pyr_conv"] = ConvWeight(P[mod(m, "weight")], P[mod(m, "bias")], dev)
+            # the same conv as "1x1 to 9 * ch_in tap-major channels, then a 9-term gather" (dsep_tap_gather3x3): row
+            # tap * ch_in + co of the 1x1 weight is W[co, :, ky, kx]; 54 rows padded to the wide-tile kernel's 128
+            wp = P[mod(m, "weight")]
+            if self.passes == 2 and wp.shape[2:] == (3, 3) and 9 * wp.shape[0] <= 128 and wp.shape[1] % 64 == 0:
+                w_taps = wp.detach().permute(2, 3, 0, 1).reshape(9 * wp.shape[0], wp.shape[1], 1, 1)
+                level["pyr_taps"] = ConvWeight(w_taps, None, dev, cout_pad=128)
+            m += 1
             if lvl != 0:
                 level["up"] = resblock(m); m += 1
             self.up.append(level)
@@ -665,7 +675,22 @@ class _Plan:
                 self.steps.append(lambda src=pyramid, Hs=h.H // 2, Ws=h.W // 2, up=up: ops.fir_resample(
                     src, B, Hs, Ws, ch_in, 1, y=up))
                 ar.release(pyramid)
-            if pyr_fused:     # GN + SiLU + split in the conv's own prologue (halo kernel, 16-column output tile)
+            taps = level.get("pyr_taps") if pyr_fused else None
+            if taps is not None and not (h.H % 32 == 0 and h.W % 8 == 0 and h.H * h.W >= PYR_TAPS_MIN_PIXELS):
+                taps = None
+            if taps is not None:
+                # maps of the wide-tile kernel: 1x1 conv (GN + SiLU + split in its prologue) to the 54 tap-major
+                # channels, then the 9-term gather adds bias and the up-sampled running pyramid
+                zc = _round_up(9 * ch_in, 4)
+                sc, sh = self._tables(st, h.C, None, 0, h.H * h.W, gam, bet)
+                z = ar.f32(B, h.H, h.W, zc)
+                self._conv_fused(h.H, h.W, h.C, taps, z, zc, h.t, h.C, None, 0, sc, sh, 1)
+                bias = level["pyr_conv"].bias
+                bias = bias[:ch_in] if bias is not None else None
+                self.steps.append(lambda z=z, Hc=h.H, Wc=h.W, zc=zc, out=new_pyr, up=up, bias=bias:
+                                  ops.tap_gather3x3(z, B, Hc, Wc, zc, ch_in, out, bias=bias, residual=up))
+                ar.release(z)
+            elif pyr_fused:     # GN + SiLU + split in the conv's own prologue (halo kernel, 16-column output tile)
                 sc, sh = self._tables(st, h.C, None, 0, h.H * h.W, gam, bet)
                 self._conv_fused(h.H, h.W, h.C, level["pyr_conv"], new_pyr, ch_in, h.t, h.C, None, 0, sc, sh, 1,
                                  residual=up)

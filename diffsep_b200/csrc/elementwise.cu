@@ -832,6 +832,80 @@ extern "C" int dsep_im2col3x3(const float* x, int B, int H, int W, int C, int Cp
     return check_launch("im2col3x3_kernel");
 }
 
+// ------------------------------------------------------------------ narrow 3x3 convolution, second half
+// A 3x3 convolution with a handful of output channels (the output pyramid's 128 / 256 -> 6, ncsnpp.py:419-440) wastes
+// the tensor core as a 3x3 problem: the full halo patch is built and nine taps run for 6 of the MMA's 16 ... 128 output
+// rows (0.95 ms at [32,256,256,128] against a 0.16 ms HBM floor).  It is run instead as
+//     z[pix][tap * CO + co] = sum_ci W[co, ci, tap] * act(x)[pix][ci]          a 1x1 conv, 9 * CO = 54 output channels,
+//     out[h, w][co] = bias[co] + residual + sum_tap z[h + ky - 1, w + kx - 1][tap * CO + co]     (this kernel)
+// i.e. the taps move from the operand side (a 9x larger K loop over a halo patch) to the output side (a 9-term gather
+// of the 1x1 result, each z element read exactly once; out-of-image neighbours are skipped: the conv zero-pads its
+// ACTIVATED input, so they contribute nothing).
+template <int COT>          // compile-time CO (6: three float2 per tap), 0 = run-time, one thread per (pixel, channel)
+__global__ void __launch_bounds__(256)
+tap_gather_kernel(const float* __restrict__ z, int H, int W, int ZC, int CO_, const float* __restrict__ bias,
+                  const float* __restrict__ residual, float* __restrict__ out, int64_t total) {
+    const int CO = COT ? COT : CO_;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t pix = static_cast<uint32_t>(COT ? e : e / CO);          // B * H * W < 2^32
+        const int c0 = COT ? 0 : static_cast<int>(e - static_cast<int64_t>(pix) * CO);
+        const uint32_t row = pix / static_cast<uint32_t>(W);                    // b * H + h
+        const int w = static_cast<int>(pix - row * static_cast<uint32_t>(W));
+        const int h = static_cast<int>(row % static_cast<uint32_t>(H));
+        constexpr int NV = COT ? COT : 1;
+        float acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = bias != nullptr ? __ldg(bias + c0 + i) : 0.f;
+        if (residual != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] += __ldg(residual + static_cast<int64_t>(pix) * CO + c0 + i);
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int hh = h + dy, ww = w + dx;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const float* q = z + (static_cast<int64_t>(pix) + dy * W + dx) * ZC + tap * CO + c0;
+            if (COT != 0 && COT % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < NV / 2; ++i) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(q) + i);
+                    acc[2 * i] += v.x;
+                    acc[2 * i + 1] += v.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc[i] += __ldg(q + i);
+            }
+        }
+        float* o = out + static_cast<int64_t>(pix) * CO + c0;
+        if (COT != 0 && COT % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) reinterpret_cast<float2*>(o)[i] = make_float2(acc[2 * i], acc[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) o[i] = acc[i];
+        }
+    }
+}
+
+extern "C" int dsep_tap_gather3x3(const float* z, int B, int H, int W, int ZC, int CO, const float* bias,
+                                  const float* residual, float* out, dsep_stream_t stream) {
+    DSEP_REQUIRE(z && out, "tap_gather3x3: null pointer");
+    DSEP_REQUIRE(B > 0 && H > 0 && W > 0 && CO > 0 && 9 * CO <= ZC, "tap_gather3x3: bad shape (9 * CO <= ZC)");
+    DSEP_REQUIRE((int64_t)B * H * W < (int64_t(1) << 32), "tap_gather3x3: tensor too large");
+    const int64_t pixels = (int64_t)B * H * W;
+    if (CO == 6 && ZC % 2 == 0) {
+        tap_gather_kernel<6><<<grid_for(pixels, 256, 148 * 64), 256, 0, (cudaStream_t)stream>>>(
+            z, H, W, ZC, CO, bias, residual, out, pixels);
+    } else {
+        const int64_t total = pixels * CO;
+        tap_gather_kernel<0><<<grid_for(total, 256, 148 * 64), 256, 0, (cudaStream_t)stream>>>(
+            z, H, W, ZC, CO, bias, residual, out, total);
+    }
+    return check_launch("tap_gather_kernel");
+}
+
 extern "C" int dsep_add(const float* a, const float* b, float* y, int64_t n, dsep_stream_t stream) {
     DSEP_REQUIRE(a && b && y && n >= 0, "add: bad arguments");
     if (n == 0) return DSEP_OK;

@@ -191,6 +191,13 @@ def im2col3x3(x, B, H, W, Cc, Cp, col):
     return col
 
 
+def tap_gather3x3(z, B, H, W, ZC, CO, out, bias=None, residual=None):
+    """out = bias + residual + sum over the 9 taps of z[neighbour][tap * CO + co] (dsep_tap_gather3x3)"""
+    call("dsep_tap_gather3x3", ptr(_f32(z, "z")), B, H, W, ZC, CO, ptr(_f32(bias, "bias")) if bias is not None else None,
+         ptr(_f32(residual, "residual")) if residual is not None else None, ptr(_f32(out, "out")), stream())
+    return out
+
+
 def add(a, b, y):
     call("dsep_add", ptr(a), ptr(b), ptr(y), a.numel(), stream())
     return y

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 6
+#define DSEP_ABI_VERSION 7
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -191,6 +191,14 @@ int dsep_combine(const float* pyr, int Cp, const float* w, const float* bias, co
  * The network's input conv (ncsnpp.py:347-349, C = 6) then runs as a 1x1 convolution with ONE 64-channel K-block
  * (dsep_conv2d_fused8 with x0 = col, no GroupNorm tables) instead of nine taps of a 6 -> 64 padded operand. */
 int dsep_im2col3x3(const float* x, int B, int H, int W, int C, int Cp, float* col, dsep_stream_t stream);
+/* Second half of a narrow 3x3 / pad 1 convolution run as "1x1 conv to 9 * CO channels, then gather": z [B,H,W,ZC] fp32
+ * with z[pix][tap * CO + co] = sum_ci W[co,ci,ky,kx] * a[pix][ci] (tap = ky * 3 + kx; produced by dsep_conv2d_fused8 with
+ * ksize 1 and the 54 tap-major weight rows) ->
+ *   out[b,h,w,co] = bias[co] + residual[b,h,w,co] + sum_tap z[b, h + ky - 1, w + kx - 1][tap * CO + co]
+ * over the neighbours inside the image; out / residual fp32 [B,H,W,CO], bias / residual may be null.  The output
+ * pyramid's conv3x3(C -> 6) (ncsnpp.py:419-440, layers.py:141-156) on maps where a halo patch per 6 channels does not pay. */
+int dsep_tap_gather3x3(const float* z, int B, int H, int W, int ZC, int CO, const float* bias,
+                       const float* residual, float* out, dsep_stream_t stream);
 int dsep_add(const float* a, const float* b, float* y, int64_t n, dsep_stream_t stream);
 
 /* ---- attention ---------------------------------------------------------------------------

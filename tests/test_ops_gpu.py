@@ -39,7 +39,7 @@ def split(ops, x, prescale=1.0):
 def test_library_loaded_and_device_ok():
     from diffsep_b200 import _lib
     lib = _lib.load()
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 7
     assert lib.dsep_device_ok() == 1
 
 
@@ -404,6 +404,80 @@ def test_im2col3x3_and_input_conv_as_1x1(shape):
     w_col = w.permute(0, 2, 3, 1).reshape(16, 9 * C)
     got = torch.einsum("bhwk,ok->bohw", col[..., :9 * C].cpu().double(), w_col.double())
     assert rel_l2(got, F.conv2d(x.double(), w.double(), padding=1)) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 6, 56), (1, 5, 9, 6, 54), (3, 7, 4, 2, 20), (1, 16, 8, 5, 48)])
+def test_tap_gather3x3(shape):
+    """dsep_tap_gather3x3: out = bias + residual + sum_tap z[pix + tap offset][tap * CO + co] over in-image neighbours.
+    With z the per-tap 1x1 products this IS the 3x3 / pad 1 convolution (checked against F.conv2d in float64); the
+    gather itself is compared with the same 9-term sum in fp32 (order ky, kx) bit for bit."""
+    ops = _ops()
+    B, H, W, CO, ZC = shape
+    g = cases.gen(sum(shape) + 5)
+    C = 16
+    a = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(CO, C, 3, 3, generator=g) / math.sqrt(9 * C)
+    bias = torch.randn(CO, generator=g)
+    res = torch.randn(B, H, W, CO, generator=g)
+    w_taps = w.permute(2, 3, 0, 1).reshape(9 * CO, C)                       # row tap * CO + co
+    z = torch.full((B, H, W, ZC), float("nan"))
+    z[..., :9 * CO] = torch.einsum("bchw,kc->bhwk", a, w_taps)
+    for bias_d, res_d in ((bias.to(DEV), res.to(DEV)), (None, None)):
+        out = torch.full((B, H, W, CO), float("nan"), device=DEV)
+        ops.tap_gather3x3(z.to(DEV), B, H, W, ZC, CO, out, bias=bias_d, residual=res_d)
+        torch.cuda.synchronize()
+        acc = torch.zeros(B, H, W, CO)
+        if bias_d is not None:
+            acc = acc + bias + res
+        zp = F.pad(torch.nan_to_num(z[..., :9 * CO]), (0, 0, 1, 1, 1, 1))
+        for tap in range(9):
+            ky, kx = tap // 3, tap % 3
+            acc = acc + zp[:, ky:ky + H, kx:kx + W, tap * CO:(tap + 1) * CO]
+        assert torch.equal(out.cpu(), acc)
+        ref = F.conv2d(a.double(), w.double(), bias.double() if bias_d is not None else None, padding=1)
+        if bias_d is not None:
+            ref = ref + res.permute(0, 3, 1, 2).double()
+        assert rel_l2(nchw(out), ref) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 128), (1, 64, 16, 256), (1, 256, 64, 64)])
+def test_narrow_conv3x3_as_1x1_plus_tap_gather(shape):
+    """The output pyramid's conv3x3(SiLU(GN(h))) -> 6 channels the way the plan runs it on large maps: the fused 1x1
+    convolution (GroupNorm + SiLU + split in its prologue, 2-unit mode, wide-tile kernel) to the 54 tap-major channels,
+    then dsep_tap_gather3x3 with the bias and the running pyramid as residual, vs float64."""
+    ops = _ops()
+    from diffsep_b200 import _lib
+    from diffsep_b200.backbone import ConvWeight
+    B, H, W, C = shape
+    CO, ZC = 6, 56
+    g = cases.gen(sum(shape) + 23)
+    x = torch.randn(B, C, H, W, generator=g) * 1.3 + 0.2
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    groups = min(C // 4, 32)
+    w = torch.randn(CO, C, 3, 3, generator=g) / math.sqrt(9 * C)
+    b1 = torch.randn(CO, generator=g) * 0.1
+    res = torch.randn(B, H, W, CO, generator=g)
+    a_ref = F.group_norm(x.double(), groups, gamma.double(), beta.double(), eps=1e-6)
+    a_ref = a_ref * torch.sigmoid(a_ref)
+    ref = F.conv2d(a_ref, w.double(), b1.double(), padding=1) + res.permute(0, 3, 1, 2).double()
+    cw = ConvWeight(w.permute(2, 3, 0, 1).reshape(9 * CO, C, 1, 1), None, DEV, cout_pad=128)
+    d = cl(x)
+    st = torch.empty(B, C, 2, dtype=torch.float64, device=DEV)
+    ops.channel_stats(d, C, B, H * W, st)
+    sc, sh = torch.empty(B, C, device=DEV), torch.empty(B, C, device=DEV)
+    ops.gn_tables(st, C, None, 0, B, H * W, groups, gamma.to(DEV), beta.to(DEV), 1e-6, sc, sh)
+    z = torch.full((B, H, W, ZC), float("nan"), device=DEV)
+    n_wide = _lib.load().dsep_conv_wide_launches()
+    ops.conv2d_fused(B, H, W, C, cw.planes8(), cw.cout_pad, 1, z, ZC, x0=d, C0=C, sc=sc, sh=sh, act=1,
+                     acc_scale=cw.acc_scale, passes=2, corr_rel=cw.corr_rel, a8_exp=cw.A8_EXP)
+    out = torch.full((B, H, W, CO), float("nan"), device=DEV)
+    ops.tap_gather3x3(z, B, H, W, ZC, CO, out, bias=b1.to(DEV), residual=res.to(DEV))
+    torch.cuda.synchronize()
+    if os.environ.get("DSEP_CONV_WIDE", "1") != "0":
+        assert _lib.load().dsep_conv_wide_launches() == n_wide + 1, "the wide-tile kernel did not take this shape"
+    assert torch.equal(z[..., 9 * CO:].cpu(), torch.zeros(B, H, W, ZC - 9 * CO))      # zero weight rows
+    assert rel_l2(nchw(out), ref) < 3e-5
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 24, 6, 128), (1, 48, 16, 6, 64), (1, 256, 64, 6, 64)])
