@@ -95,7 +95,7 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self.window = torch.hann_window(self.n_fft, dtype=torch.float32).to(self.dev)
         self.basis_fwd, self.basis_inv = _dft_bases(self.n_fft, self.dev)
         # DFT-510 / inverse as a 1x1 "convolution" on the tensor core (three fp16 products, fp32-grade: the row
-        # matrix [M, 512] is the image [1, M/8, 8, 512]) instead of the fp32 CUDA-core GEMM, when M % 8 == 0
+        # matrix [M, 512], rows padded to whole 8-row lines, is the image [1, M/8, 8, 512]) instead of the fp32 CUDA-core GEMM
         self._stft_tc = bool(int(os.environ.get("DSEP_STFT_TC", "1"))) and cin_align() == 64
         self._basis_cw = {}
         if self._stft_tc:      # built now (allocations + a host sync), never inside a CUDA-graph capture
@@ -124,14 +124,25 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self._film_cache = {}
         return self
 
+    @staticmethod
+    def dft_rows(M):
+        """rows the tensor-core form of the DFT product works on: whole 8-row image lines, at least 16 of them"""
+        return max(128, (M + 7) // 8 * 8)
+
     def _dft(self, src, which, dst, M):
-        """dst[M, LD] = src[M, LD] @ basis (``which``: "fwd" / "inv")."""
+        """dst[M, LD] = src[M, LD] @ basis (``which``: "fwd" / "inv").
+
+        Tensor-core form whenever the buffers hold ``dft_rows(M)`` rows (the model's own buffers always do: the pad
+        rows are zero and each output row depends on its own input row only), so that the arithmetic does NOT depend
+        on the batch size — a shard of a batch must reproduce the whole batch's results (tests/test_graded_gpu.py,
+        2-GPU gather).  Exact-size buffers of other callers fall back to the fp32 GEMM when M is not such a count."""
         basis = self.basis_fwd if which == "fwd" else self.basis_inv
-        if not (self._stft_tc and M % 8 == 0 and M >= 128):
+        Mp = self.dft_rows(M)
+        if not (self._stft_tc and src.shape[0] >= Mp and dst.shape[0] >= Mp):
             ops.sgemm(src, LD, basis, LD, dst, LD, M, LD, LD)
             return
         cw = self._basis_cw[which]
-        ops.conv2d_fused(1, M // 8, 8, LD, cw.planes, cw.cout_pad, 1, dst, LD, x0=src, C0=LD, act=0,
+        ops.conv2d_fused(1, Mp // 8, 8, LD, cw.planes, cw.cout_pad, 1, dst, LD, x0=src, C0=LD, act=0,
                          acc_scale=cw.acc_scale, passes=3)
 
     # -------------------------------------------------------------- buffers per (B, T)
@@ -152,15 +163,16 @@ class ScoreModelNCSNpp(torch.nn.Module):
         Fr = n_frames(T)
         Wp = (Fr + 63) // 64 * 64
         f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        rows = lambda m: torch.zeros(self.dft_rows(m), LD, device=dev, dtype=torch.float32)   # operands of _dft
         b = dict(
             Fr=Fr, Wp=Wp,
-            frames=f32(B * ns * Fr, LD), dft=f32(B * ns * Fr, LD),
-            frames_mix=f32(B * Fr, LD), dft_mix=f32(B * Fr, LD),
+            frames=rows(B * ns * Fr), dft=rows(B * ns * Fr),
+            frames_mix=rows(B * Fr), dft_mix=rows(B * Fr),
             # operand planes of the input conv — not needed when it runs over im2col rows of x_pyr
             x_planes=(None if self.backbone.conv_in_col is not None
                       else Split.zeros((B, N_BINS, Wp, self.backbone.conv_in.cin_pad), dev)),
             x_pyr=f32(B, N_BINS, Wp, self.ch_in),
-            spec_out=f32(B * ns * Fr, LD), frames_out=f32(B * ns * Fr, LD),
+            spec_out=rows(B * ns * Fr), frames_out=rows(B * ns * Fr),
             score=f32(B, ns, T),
         )
         self._bufs[key] = b

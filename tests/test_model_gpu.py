@@ -633,20 +633,31 @@ def test_compute_score_loss_forward_vs_oracle():
 def test_stft_gemms_on_the_tensor_core_match_the_fp32_gemm():
     """ScoreModelNCSNpp._dft: the DFT-510 / inverse products as a 1x1 convolution with three fp16 tensor-core products
     (fp32-grade) against the fp32 CUDA-core GEMM and a float64 product, forward and inverse, at the benchmark's row
-    count (B * ns * Fr = 64 * 251) and at a row count that falls back to the GEMM (M % 8 != 0)."""
+    count (B * ns * Fr = 64 * 251), at row counts that are not whole 8-row lines / fewer than 128 with the model's padded
+    buffers (still the tensor core: the arithmetic must not depend on the batch size, so a row's result is the same
+    bit for bit whatever the batch it sits in), and with exact-size buffers (falls back to the GEMM)."""
     from diffsep_b200 import ops
     from diffsep_b200.score_model import ScoreModelNCSNpp, LD
     sm = ScoreModelNCSNpp(num_sources=2, backbone_args=dict(nf=64))
     g = cases.gen(5)
-    for M in (64 * 251, 2 * 251):
-        src = torch.randn(M, LD, generator=g).to(DEV)
+    for M, padded in ((64 * 251, True), (2 * 251, True), (65, True), (2 * 251, False)):
+        Mb = sm.dft_rows(M) if padded else M
+        src = torch.zeros(Mb, LD, device=DEV)
+        src[:M] = torch.randn(M, LD, generator=g).to(DEV)
         src[:, 510:] = 0.0
         for which, basis in (("fwd", sm.basis_fwd), ("inv", sm.basis_inv)):
-            want = (src.double() @ basis.double()).cpu()
+            want = (src[:M].double() @ basis.double()).cpu()
             ref = torch.empty(M, LD, device=DEV)
             ops.sgemm(src, LD, basis, LD, ref, LD, M, LD, LD)
-            got = torch.full((M, LD), float("nan"), device=DEV)
+            got = torch.full((Mb, LD), float("nan"), device=DEV)
             sm._dft(src, which, got, M)
             torch.cuda.synchronize()
             assert rel_l2(ref.cpu(), want) < 1e-6
-            assert rel_l2(got.cpu(), want) < 2e-6, (M, which)
+            assert rel_l2(got[:M].cpu(), want) < 2e-6, (M, which)
+            if padded:      # a row's result does not depend on how many rows come with it
+                big = torch.zeros(sm.dft_rows(4 * M), LD, device=DEV)
+                big[M:2 * M] = src[:M]
+                out = torch.empty_like(big)
+                sm._dft(big, which, out, 4 * M)
+                torch.cuda.synchronize()
+                assert torch.equal(out[M:2 * M], got[:M]), (M, which)
