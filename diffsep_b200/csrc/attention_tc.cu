@@ -120,33 +120,84 @@ attention_tc_kernel(const float* __restrict__ qkv, int S, int C, float scale, __
         umma_commit(bar);
     };
 
+    // Operand tiles travel global -> registers -> (split) -> shared memory.  The loads of the NEXT tile are issued right
+    // after this tile's Q K^T goes to the tensor core and land while the MMAs, the TMEM read and the softmax run; the
+    // first version loaded, converted and stored each tile inside the iteration (pass 2: four dependent batches of
+    // strided V loads), i.e. every one of the 2 * S / 32 iterations waited out several global-memory round trips
+    // (92 us at S = 256, profiles/levels_r2k.md).
+    const int chunks = C >> 3;                       // 8-channel chunks per K row
+    const int k_items = kAK * chunks;                // (row, chunk) items of a K tile: C / 64 per thread
+    float4 rk[4][2];
+    float rv[kAK];
+    auto fetch = [&](int pass_, int t_) {
+        const int j0 = t_ * kAK;
+        const int nk = min(kAK, S - j0);
+        const float* kp = base + static_cast<size_t>(j0) * pitch + C;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = tid + u * kAThreads;
+            rk[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rk[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < k_items) {
+                const int row = idx / chunks, ch = idx - row * chunks;
+                if (row < nk) {
+                    rk[u][0] = __ldg(reinterpret_cast<const float4*>(kp + row * pitch + ch * 8));
+                    rk[u][1] = __ldg(reinterpret_cast<const float4*>(kp + row * pitch + ch * 8 + 4));
+                }
+            }
+        }
+        if (pass_ == 1 && tid < C) {                 // thread <-> channel d: the 32 keys of V[:, d] (C <= 256)
+            const float* vcol = base + static_cast<size_t>(j0) * pitch + 2 * C + tid;
+#pragma unroll
+            for (int i = 0; i < kAK; ++i) rv[i] = (i < nk) ? __ldg(vcol + i * pitch) : 0.0f;
+        }
+    };
+    // registers -> split planes: K rows (128B-swizzled, C/64 K-blocks of [32 x 128 B]); pass 2 also row d of V^T
+    // (64B-swizzled, 4 chunks of 8 keys).  Rows / keys beyond the sequence arrive as zeros.
+    auto stash = [&](int pass_) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = tid + u * kAThreads;
+            if (idx < k_items) {
+                const int row = idx / chunks, ch = idx - row * chunks;
+                uint32_t hi[4], lo[4];
+                split2h(rk[u][0].x, rk[u][0].y, hi[0], lo[0]); split2h(rk[u][0].z, rk[u][0].w, hi[1], lo[1]);
+                split2h(rk[u][1].x, rk[u][1].y, hi[2], lo[2]); split2h(rk[u][1].z, rk[u][1].w, hi[3], lo[3]);
+                const int kb = ch >> 3, j = ch & 7;
+                const uint32_t off = static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+                const uint32_t p_hi = k_base + static_cast<uint32_t>(kb * 2) * (kAK * 128u);
+                sts128u(p_hi + off, hi[0], hi[1], hi[2], hi[3]);
+                sts128u(p_hi + kAK * 128u + off, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        if (pass_ == 1 && tid < C) {
+            const int d = tid;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2h(rv[c * 8 + 2 * i], rv[c * 8 + 2 * i + 1], hi[i], lo[i]);
+                const uint32_t off = static_cast<uint32_t>(d) * 64u + (static_cast<uint32_t>(c ^ ((d >> 1) & 3)) << 4);
+                sts128u(v_base + off, hi[0], hi[1], hi[2], hi[3]);
+                sts128u(v_base + static_cast<uint32_t>(C) * 64u + off, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    };
+
+    fetch(0, 0);
     for (int pass = 0; pass < 2; ++pass) {
         for (int t = 0; t < n_tiles; ++t) {
             const int j0 = t * kAK;
             const int nk = min(kAK, S - j0);
-            // ---- operands of this tile: K rows (split, 128B-swizzled); pass 2 also V^T (split, 64B-swizzled)
-            load_split_rows<kAK>(base + static_cast<size_t>(j0) * pitch + C, pitch, nk, C, k_base, tid);
-            if (pass == 1) {
-                // thread <-> channel d: 32 keys of V[:, d] -> row d of V^T (4 chunks of 8 keys)
-                for (int d = tid; d < C; d += kAThreads) {
-                    const float* vcol = base + static_cast<size_t>(j0) * pitch + 2 * C + d;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = (c * 8 + i < nk) ? __ldg(vcol + (c * 8 + i) * pitch) : 0.0f;
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split2h(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-                        const uint32_t off = static_cast<uint32_t>(d) * 64u + (static_cast<uint32_t>(c ^ ((d >> 1) & 3)) << 4);
-                        sts128u(v_base + off, hi[0], hi[1], hi[2], hi[3]);
-                        sts128u(v_base + static_cast<uint32_t>(C) * 64u + off, lo[0], lo[1], lo[2], lo[3]);
-                    }
-                }
-            }
+            // ---- operands of this tile out of the registers (the K / V^T / P buffers are free: the previous
+            //      iteration ended with a barrier after its last reader)
+            stash(pass);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             if (tid == 0) { tc_fence_after(); issue_qk(); }
+            // the next tile's loads (pass 1's first tile follows pass 0's last) fly during the MMAs and the softmax
+            if (t + 1 < n_tiles) fetch(pass, t + 1);
+            else if (pass == 0) fetch(1, 0);
             mbar_wait(bar, phase);
             phase ^= 1u;
             tc_fence_after();
