@@ -94,13 +94,15 @@ class ScoreModelNCSNpp(torch.nn.Module):
         self.backbone = None
         self.window = torch.hann_window(self.n_fft, dtype=torch.float32).to(self.dev)
         self.basis_fwd, self.basis_inv = _dft_bases(self.n_fft, self.dev)
-        # DFT-510 / inverse as a 1x1 "convolution" on the tensor core (three fp16 products, fp32-grade: the row
-        # matrix [M, 512], rows padded to whole 8-row lines, is the image [1, M/8, 8, 512]) instead of the fp32 CUDA-core GEMM
+        # forward DFT-510 as a 1x1 "convolution" on the tensor core (three fp16 products, fp32-grade: the row
+        # matrix [M, 512], rows padded to whole 8-row lines, is the image [1, M/8, 8, 512]) instead of the fp32 CUDA-core
+        # GEMM.  Only the FORWARD product: its operand is windowed audio, O(1).  The inverse product's operand is the
+        # decompressed score spectrogram ((|z| / 0.15)^2: 2e5 and more with the synthetic weights of the tests, unbounded
+        # in general), beyond what an fp16 (hi, lo) pair represents (2 x 65504) — it stays an fp32 GEMM.
         self._stft_tc = bool(int(os.environ.get("DSEP_STFT_TC", "1"))) and cin_align() == 64
         self._basis_cw = {}
         if self._stft_tc:      # built now (allocations + a host sync), never inside a CUDA-graph capture
-            for which, basis in (("fwd", self.basis_fwd), ("inv", self.basis_inv)):
-                self._basis_cw[which] = ConvWeight(basis.t().contiguous().reshape(LD, LD, 1, 1), None, self.dev)
+            self._basis_cw["fwd"] = ConvWeight(self.basis_fwd.t().contiguous().reshape(LD, LD, 1, 1), None, self.dev)
         self._bufs = {}
         self._mix_cache = None     # (data_ptr, B, T) of the mixture whose spectrogram is resident
         self._mix_cache_on = False
@@ -132,13 +134,13 @@ class ScoreModelNCSNpp(torch.nn.Module):
     def _dft(self, src, which, dst, M):
         """dst[M, LD] = src[M, LD] @ basis (``which``: "fwd" / "inv").
 
-        Tensor-core form whenever the buffers hold ``dft_rows(M)`` rows (the model's own buffers always do: the pad
+        Forward product: tensor-core form whenever the buffers hold ``dft_rows(M)`` rows (the model's own always do: the pad
         rows are zero and each output row depends on its own input row only), so that the arithmetic does NOT depend
         on the batch size — a shard of a batch must reproduce the whole batch's results (tests/test_graded_gpu.py,
         2-GPU gather).  Exact-size buffers of other callers fall back to the fp32 GEMM when M is not such a count."""
         basis = self.basis_fwd if which == "fwd" else self.basis_inv
         Mp = self.dft_rows(M)
-        if not (self._stft_tc and src.shape[0] >= Mp and dst.shape[0] >= Mp):
+        if not (which in self._basis_cw and src.shape[0] >= Mp and dst.shape[0] >= Mp):
             ops.sgemm(src, LD, basis, LD, dst, LD, M, LD, LD)
             return
         cw = self._basis_cw[which]
