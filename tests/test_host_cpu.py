@@ -369,3 +369,15 @@ def test_numerics_study_e4m3_emulator_matches_torch_float8():
     k = math.floor(math.log2(448.0 / float(x.abs().max())))
     ref = (x * 2.0 ** k).float().clamp(-448, 448).to(torch.float8_e4m3fn).double() * 2.0 ** -k
     assert torch.equal(ns.e4m3(x), ref)
+
+
+def test_dft_row_padding_is_batch_size_independent():
+    """ScoreModelNCSNpp.dft_rows: the forward DFT product always runs in its tensor-core form on whole 8-row lines
+    (at least 128 rows), so the arithmetic a spectrogram row sees cannot depend on how many utterances share the
+    batch — a shard must reproduce the whole batch (the 2-GPU gather test on hardware)."""
+    from diffsep_b200.score_model import ScoreModelNCSNpp
+    r = ScoreModelNCSNpp.dft_rows
+    for m in (1, 63, 126, 127, 128, 129, 260, 520, 16064):
+        assert r(m) >= max(m, 128) and r(m) % 8 == 0 and r(m) - m < 128
+    assert r(260) == 264 and r(520) == 520 and r(65) == 128
+
