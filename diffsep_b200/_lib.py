@@ -15,7 +15,7 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("DSEP_LIB") or Path(__file__).resolve().parent / "libdsep.so")
 
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _p, _i, _f, _i64, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -51,7 +51,7 @@ PROTOTYPES = {
     "dsep_fir_resample8": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _i, _p],
     "dsep_fir_resample_f32": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p],
     "dsep_upfirdn2d": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
-    "dsep_combine": [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p],
+    "dsep_combine": [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p],
     "dsep_add": [_p, _p, _p, _i64, _p],
     "dsep_im2col3x3": [_p, _i, _i, _i, _i, _i, _p, _p],
     "dsep_tap_gather3x3": [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p],

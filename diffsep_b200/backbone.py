@@ -633,8 +633,12 @@ class _Plan:
                     ar.release(src)
                 pyr_in = new_pyr
                 cw, cb = level["combine"]
-                self.steps.append(lambda pyr=new_pyr, cw=cw, cb=cb, t=h.t, P=h.H * h.W, c=h.C: ops.combine(
-                    pyr, ch_in, cw, cb, t, t, B, P, c))
+                # maps whose consumers would otherwise launch channel_stats on the combined tensor: the sums are taken
+                # here (small maps: the consuming gn_act_split computes them itself, _stats_or_defer)
+                if h.st is None and h.H * h.W > 64 and int(os.environ.get("DSEP_COMBINE_STATS", "1")):
+                    h.st = self._slot(h.C)
+                self.steps.append(lambda pyr=new_pyr, cw=cw, cb=cb, t=h.t, P=h.H * h.W, c=h.C, st=h.st: ops.combine(
+                    pyr, ch_in, cw, cb, t, t, B, P, c, stats=st))
                 H, W = h.H, h.W
                 hs.append(h)
         if pyr_in is not None:

@@ -494,30 +494,57 @@ fir_scalar_kernel(const float* __restrict__ x, int64_t total_out, int H, int W, 
 // weights are staged transposed, s_w[k][c]: a warp reads 32 consecutive channel quads of one k with one
 // conflict-free LDS.128 per lane (the [c][k] order put the lanes' words 24 floats apart: 8-way bank conflicts,
 // 1.5 TB/s; profiles/membound_r2a.md)
+// grid (chunks, B): a block owns a run of pixels of ONE batch entry, so that the per-channel (sum, sum of squares) of
+// its outputs — the statistics of the GroupNorm that consumes the combined tensor — leave the block once (fp64,
+// accumulated like channel_stats_kernel does) instead of costing a channel_stats launch and a second read of `out`.
 __global__ void __launch_bounds__(256)
 combine_kernel(const float* __restrict__ pyr, int Cp, const float* __restrict__ w,
                const float* __restrict__ bias, const float* __restrict__ h, float* __restrict__ out,
-               int64_t total_quads, int C) {
-    extern __shared__ __align__(16) float s_w[];   // [Cp][C] + [C]
+               int P, int C, int pix_per_block, double* __restrict__ stats) {
+    extern __shared__ __align__(16) float s_w[];   // [Cp][C] + [C] (+ [C][2] doubles when stats are taken)
     float* s_b = s_w + C * Cp;
+    double* s_acc = reinterpret_cast<double*>(s_b + C);
     for (int i = threadIdx.x; i < C * Cp; i += blockDim.x) s_w[(i % Cp) * C + i / Cp] = w[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+    if (stats != nullptr)
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
-    const int Q = C >> 2;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total_quads;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int q = static_cast<int>(e % Q);
-        const int64_t pix = e / Q;
+    const int Q = C >> 2, b = blockIdx.y;
+    const int ppi = blockDim.x / Q;                 // pixels per iteration (threads beyond ppi * Q idle)
+    const int q = threadIdx.x % Q, j = threadIdx.x / Q;
+    if (j < ppi) {
         const int c = q * 4;
-        float4 v = __ldg(reinterpret_cast<const float4*>(h) + e);
-        float4 a = *reinterpret_cast<const float4*>(s_b + c);
-        for (int k = 0; k < Cp; ++k) {
-            const float pk = __ldg(pyr + pix * Cp + k);
-            const float4 wk = *reinterpret_cast<const float4*>(s_w + k * C + c);
-            a.x = fmaf(wk.x, pk, a.x); a.y = fmaf(wk.y, pk, a.y); a.z = fmaf(wk.z, pk, a.z); a.w = fmaf(wk.w, pk, a.w);
+        const int p_begin = blockIdx.x * pix_per_block;
+        const int p_end = min(P, p_begin + pix_per_block);
+        double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int p = p_begin + j; p < p_end; p += ppi) {
+            const int64_t pix = static_cast<int64_t>(b) * P + p;
+            const int64_t e = pix * Q + q;
+            float4 v = __ldg(reinterpret_cast<const float4*>(h) + e);
+            float4 a = *reinterpret_cast<const float4*>(s_b + c);
+            for (int k = 0; k < Cp; ++k) {
+                const float pk = __ldg(pyr + pix * Cp + k);
+                const float4 wk = *reinterpret_cast<const float4*>(s_w + k * C + c);
+                a.x = fmaf(wk.x, pk, a.x); a.y = fmaf(wk.y, pk, a.y); a.z = fmaf(wk.z, pk, a.z); a.w = fmaf(wk.w, pk, a.w);
+            }
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            reinterpret_cast<float4*>(out)[e] = v;
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            ss[0] += (double)v.x * v.x; ss[1] += (double)v.y * v.y;
+            ss[2] += (double)v.z * v.z; ss[3] += (double)v.w * v.w;
         }
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        reinterpret_cast<float4*>(out)[e] = v;
+        if (stats != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                atomicAdd(&s_acc[(c + u) * 2 + 0], s[u]);
+                atomicAdd(&s_acc[(c + u) * 2 + 1], ss[u]);
+            }
+        }
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+            atomicAdd(&stats[static_cast<size_t>(b) * 2 * C + i], s_acc[i]);
     }
 }
 
@@ -778,12 +805,14 @@ extern "C" int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_
 }
 
 extern "C" int dsep_combine(const float* pyr, int Cp, const float* w, const float* bias, const float* h,
-                            float* out, int B, int P, int C, dsep_stream_t stream) {
+                            float* out, int B, int P, int C, double* stats, dsep_stream_t stream) {
     DSEP_REQUIRE(pyr && w && h && out, "combine: null pointer");
-    DSEP_REQUIRE(B > 0 && P > 0 && C > 0 && C % 4 == 0 && Cp > 0 && Cp <= 16, "combine: bad shape");
-    const int64_t total = (int64_t)B * P * (C / 4);
-    const size_t smem = sizeof(float) * (C * Cp + C);
-    combine_kernel<<<grid_for(total), 256, smem, (cudaStream_t)stream>>>(pyr, Cp, w, bias, h, out, total, C);
+    DSEP_REQUIRE(B > 0 && B <= 65535 && P > 0 && C > 0 && C % 4 == 0 && C <= 1024 && Cp > 0 && Cp <= 16,
+                 "combine: bad shape");
+    const int ppb = pix_per_block_for(P, B);
+    dim3 grid(ceil_div(P, ppb), B);
+    const size_t smem = sizeof(float) * (C * Cp + C) + (stats ? sizeof(double) * 2 * C : 0);
+    combine_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pyr, Cp, w, bias, h, out, P, C, ppb, stats);
     return check_launch("combine_kernel");
 }
 

@@ -181,8 +181,11 @@ def upfirdn2d_planes(x, planes, H, W, up, down, pad, out):
     return out
 
 
-def combine(pyr, Cp, w, bias, h, out, B, P, Cc):
-    call("dsep_combine", ptr(pyr), Cp, ptr(w), ptr(bias), ptr(h), ptr(out), B, P, Cc, stream())
+def combine(pyr, Cp, w, bias, h, out, B, P, Cc, stats=None):
+    """``stats`` (fp64 [B, Cc, 2], zeroed by the caller): the per-channel sums of ``out`` are added to it"""
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != B * Cc * 2):
+        raise ValueError("combine: stats must be float64 [B, C, 2]")
+    call("dsep_combine", ptr(pyr), Cp, ptr(w), ptr(bias), ptr(h), ptr(out), B, P, Cc, ptr(stats), stream())
     return out
 
 

@@ -31,7 +31,7 @@ extern "C" {
 #define DSEP_ERR_CUDA (-2)        /* CUDA runtime/driver error (wrappers raise RuntimeError)  */
 #define DSEP_ERR_UNSUPPORTED (-3) /* valid in the reference but outside the hot path's shapes */
 
-#define DSEP_ABI_VERSION 7
+#define DSEP_ABI_VERSION 8
 
 typedef void* dsep_stream_t; /* cudaStream_t */
 
@@ -182,9 +182,11 @@ int dsep_upfirdn2d(const float* in, int planes, int H, int W, int up_x, int up_y
                    dsep_stream_t stream);
 
 /* out = h + bias + conv1x1(pyr): Combine(method="sum") (layerspp.py:52-57). pyr fp32 [B,P,Cp],
- * w fp32 [C,Cp]. */
+ * w fp32 [C,Cp]; out may alias h.  stats (nullable): fp64 [B,C,2], the per-channel (sum, sum of squares) of `out` are
+ * ADDED to it (zero it first) — the statistics of the GroupNorm that reads the combined tensor (layerspp.py:291-296),
+ * taken here instead of by a dsep_channel_stats pass over `out`. */
 int dsep_combine(const float* pyr, int Cp, const float* w, const float* bias, const float* h,
-                 float* out, int B, int P, int C, dsep_stream_t stream);
+                 float* out, int B, int P, int C, double* stats, dsep_stream_t stream);
 /* y = a + b (fp32, n elements): pyramid accumulation (ncsnpp.py:440). */
 /* im2col rows of a 3x3 / pad 1 convolution with few input channels: x [B,H,W,C] fp32 -> col [B,H,W,Cp] fp32,
  * col[pix][tap * C + c] = x[pix + tap offset][c] (zero outside the image and for columns >= 9 * C; tap = ky * 3 + kx).

@@ -30,7 +30,7 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.PROTOTYPES) | set(_lib.OTHER_SYMBOLS)
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 8
 
 
 def test_abi_argument_counts_match_header():

@@ -39,7 +39,7 @@ def split(ops, x, prescale=1.0):
 def test_library_loaded_and_device_ok():
     from diffsep_b200 import _lib
     lib = _lib.load()
-    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.dsep_abi_version() == _lib.ABI_VERSION == 8
     assert lib.dsep_device_ok() == 1
 
 
@@ -762,6 +762,22 @@ def test_combine():
     ops.combine(pyr.to(DEV), Cp, w.to(DEV), b.to(DEV), h.to(DEV), out, B, P, C)
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), ref) < 1e-6
+    # in place (out aliases h, as the plan calls it) with the consuming GroupNorm's sums taken on the way; other sizes
+    for B2, P2, C2 in ((3, 1000, 64), (2, 16384, 128), (1, 77, 256)):
+        pyr2, h2 = torch.randn(B2, P2, Cp, generator=g), torch.randn(B2, P2, C2, generator=g)
+        w2, b2 = torch.randn(C2, Cp, generator=g), torch.randn(C2, generator=g)
+        ref2 = h2.double() + pyr2.double() @ w2.double().t() + b2.double()
+        hd = h2.to(DEV)
+        plain = torch.empty(B2, P2, C2, device=DEV)
+        ops.combine(pyr2.to(DEV), Cp, w2.to(DEV), b2.to(DEV), hd, plain, B2, P2, C2)
+        stats = torch.zeros(B2, C2, 2, dtype=torch.float64, device=DEV)
+        ops.combine(pyr2.to(DEV), Cp, w2.to(DEV), b2.to(DEV), hd, hd, B2, P2, C2, stats=stats)
+        torch.cuda.synchronize()
+        assert torch.equal(hd, plain)
+        assert rel_l2(hd.cpu(), ref2) < 1e-6
+        got = hd.double().cpu()
+        assert rel_l2(stats[..., 0].cpu(), got.sum(dim=1)) < 1e-9
+        assert rel_l2(stats[..., 1].cpu(), (got * got).sum(dim=1)) < 1e-9
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 128), (2, 256, 128), (2, 120, 128), (3, 256, 256), (2, 1920, 256),
