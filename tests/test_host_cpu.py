@@ -381,3 +381,26 @@ def test_dft_row_padding_is_batch_size_independent():
         assert r(m) >= max(m, 128) and r(m) % 8 == 0 and r(m) - m < 128
     assert r(260) == 264 and r(520) == 520 and r(65) == 128
 
+
+def test_narrow_conv_as_1x1_plus_tap_gather_algebra():
+    """The layout convention of the output-pyramid convs on large maps (backbone.py ``pyr_taps`` + dsep_tap_gather3x3,
+    ncsnpp.py:419-440): row ``tap * CO + co`` of the 1x1 weight is ``W[co, :, ky, kx]`` (tap = ky * 3 + kx) and
+    ``out[h, w, co] = bias[co] + sum_tap z[h + ky - 1, w + kx - 1, tap * CO + co]`` over in-image neighbours — checked
+    here in plain torch against F.conv2d, so the convention the CUDA gather implements is pinned without a GPU."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W, CO = 2, 16, 7, 9, 6
+    a = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(CO, C, 3, 3, generator=g, dtype=torch.float64)
+    bias = torch.randn(CO, generator=g, dtype=torch.float64)
+    w_taps = w.permute(2, 3, 0, 1).reshape(9 * CO, C, 1, 1)              # what backbone.py feeds the 1x1 convolution
+    z = F.conv2d(a, w_taps)                                              # [B, 54, H, W]
+    zp = F.pad(z, (1, 1, 1, 1))
+    out = bias.view(1, CO, 1, 1).expand(B, CO, H, W).clone()
+    for tap in range(9):
+        ky, kx = tap // 3, tap % 3
+        out += zp[:, tap * CO:(tap + 1) * CO, ky:ky + H, kx:kx + W]
+    ref = F.conv2d(a, w, bias, padding=1)
+    assert float((out - ref).abs().max()) < 1e-12
+
